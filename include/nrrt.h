@@ -1,0 +1,369 @@
+/*
+ * nrrt.h — C ABI of the B200-native path-tracing hot path of nr-ray-tracer.
+ *
+ * The reference has no FFI boundary: its hot path is the generic Rust call
+ *   Scene::render(&self, progress) -> Rgb32FImage        (packages/ray-tracer-lib/src/scene.rs:13-18)
+ *     -> Camera::render(&self, hitable, progress)        (packages/ray-tracer-lib/src/camera.rs:302-343)
+ * whose only caller is  packages/ray-tracer/src/commands/render.rs:59.
+ * This header defines the boundary a Rust `-sys` crate would bind (see
+ * INTEGRATION.md): plain pointers and sizes only, caller-owned host buffers,
+ * every device allocation owned by the context, integer status codes.
+ *
+ * Two layers:
+ *   1. "graph" layer  (nrrt_graph_*)  — a description of the reference's object
+ *      graph (what CLI scene_config.rs:278-380 builds): spheres, quads,
+ *      triangles, groups (= BVH::from), translate/rotate/scale wrappers,
+ *      materials, textures.  nrrt_host_build() runs the reference's BVH build
+ *      (objects/object.rs:41-73) on the host and flattens the tree into ...
+ *   2. "flat" layer   (nrrt_scene_desc) — the structure-of-arrays device layout
+ *      (64-byte two-child f32 nodes + exact f64 boxes, primitive SoA, instance
+ *      transform chains, material/texture tables) that nrrt_scene_upload()
+ *      copies to HBM and the CUDA kernels traverse.
+ *
+ * All geometry is f64 like the reference; f32 appears only in conservative
+ * culling boxes and the output framebuffer.
+ */
+#ifndef NRRT_H
+#define NRRT_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRRT_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+    NRRT_OK = 0,
+    NRRT_ERR_INVALID = -1,   /* bad argument / malformed scene            */
+    NRRT_ERR_CUDA = -2,      /* CUDA runtime failure (see nrrt_last_error) */
+    NRRT_ERR_NO_DEVICE = -3, /* no usable GPU: there is NO CPU fallback    */
+    NRRT_ERR_NO_SCENE = -4,  /* render/trace before nrrt_scene_upload      */
+    NRRT_ERR_LIMIT = -5,     /* scene exceeds a compiled-in limit          */
+    NRRT_ERR_IO = -6         /* scene file / texture could not be read     */
+};
+
+/* ======================================================================== */
+/* 1. graph layer: mirror of ObjectConfig / MaterialConfig / TextureConfig  */
+/*    after id resolution (CLI scene_config.rs:27-259).                     */
+/* ======================================================================== */
+
+enum nrrt_obj_kind {
+    NRRT_OBJ_SPHERE = 0,    /* v[0..2]=center v[3]=radius       objects/sphere.rs:69-91   */
+    NRRT_OBJ_QUAD = 1,      /* v[0..2]=p v[3..5]=u v[6..8]=v    objects/plane.rs:95-127   */
+    NRRT_OBJ_TRIANGLE = 2,  /* same as quad, Shape::Triangle                              */
+    NRRT_OBJ_GROUP = 3,     /* BVH::from(children)  (Group, Scene, and the scene list)    */
+    NRRT_OBJ_TRANSLATE = 4, /* v[0..2]=offset, one child        objects/translate.rs      */
+    NRRT_OBJ_ROTATE_X = 5,  /* v[0]=angle (radians), one child  objects/rotate.rs:47-62   */
+    NRRT_OBJ_ROTATE_Y = 6,
+    NRRT_OBJ_ROTATE_Z = 7,
+    NRRT_OBJ_SCALE = 8      /* v[0..2]=scale vector, one child  objects/scale.rs:44-58    */
+};
+
+typedef struct nrrt_object {
+    uint32_t kind;        /* nrrt_obj_kind */
+    uint32_t material;    /* index into materials (primitives only) */
+    uint32_t first_child; /* index into nrrt_graph_desc.child_ids */
+    uint32_t n_children;  /* groups: any; wrappers: 1; primitives: 0 */
+    double v[9];
+} nrrt_object;
+
+enum nrrt_material_kind {
+    NRRT_MAT_LAMBERTIAN = 0,    /* materials/lambertian.rs:39-55                    */
+    NRRT_MAT_METAL = 1,         /* param = fuzz        materials/metal.rs:73-91     */
+    NRRT_MAT_DIELECTRIC = 2,    /* param = ior         materials/dielectric.rs:39-67 */
+    NRRT_MAT_DIFFUSE_LIGHT = 3  /* param = intensity   materials/diffuse_light.rs:63-75 */
+};
+
+typedef struct nrrt_material {
+    uint32_t kind;
+    uint32_t texture; /* index into textures (ignored by dielectric) */
+    double param;
+} nrrt_material;
+
+enum nrrt_texture_kind {
+    NRRT_TEX_SOLID = 0,   /* color                                   textures/solid_color.rs */
+    NRRT_TEX_CHECKER = 1, /* a=even texture, b=odd texture, f0=scale textures/checker.rs:77-89 */
+    NRRT_TEX_IMAGE = 2,   /* a=image index                           textures/image.rs:30-40 */
+    NRRT_TEX_NOISE = 3,   /* |Fbm<Perlin>|: seed, octaves, f0=frequency, f1=lacunarity,
+                             f2=persistence                          textures/noise.rs:79-145 */
+    NRRT_TEX_MARBLE = 4   /* seed, f0=frequency (7 octaves)          textures/marble.rs:46-97 */
+};
+
+typedef struct nrrt_texture {
+    uint32_t kind;
+    uint32_t a, b;
+    uint32_t seed;
+    uint32_t octaves;
+    uint32_t _pad;
+    double color[3];
+    double f0, f1, f2;
+} nrrt_texture;
+
+/* Decoded 8-bit RGB image, row-major, 3 bytes per texel, row 0 = top.
+ * The reference converts with into_rgb32f() = u8/255 as f32 (textures/image.rs:24). */
+typedef struct nrrt_image {
+    uint32_t width, height;
+    const uint8_t* rgb;
+} nrrt_image;
+
+typedef struct nrrt_graph_desc {
+    uint32_t n_objects;
+    const nrrt_object* objects;
+    uint32_t n_child_ids;
+    const uint32_t* child_ids;
+    uint32_t n_materials;
+    const nrrt_material* materials;
+    uint32_t n_textures;
+    const nrrt_texture* textures;
+    uint32_t n_images;
+    const nrrt_image* images;
+    uint32_t root; /* object index of the scene list (a GROUP): Scene.objects = BVH::from(list) */
+} nrrt_graph_desc;
+
+/* CameraBuilder fields (camera.rs:30-41); angles in RADIANS (the CLI converts
+ * degrees at cli.rs:369-379 before they reach the builder). */
+typedef struct nrrt_camera_config {
+    uint32_t width, height;
+    uint32_t samples_per_pixel, ray_max_bounces;
+    double background[3];
+    double look_from[3], look_at[3], view_up[3];
+    double defocus_angle, focus_dist, field_of_view;
+} nrrt_camera_config;
+
+/* The built Camera (camera.rs:206-227): what the kernels consume. */
+typedef struct nrrt_camera {
+    uint32_t width, height;
+    uint32_t samples_per_pixel, ray_max_bounces;
+    double background[3];
+    double look_from[3];
+    double defocus_disk_u[3], defocus_disk_v[3];
+    double pixel_delta_u[3], pixel_delta_v[3];
+    double viewport_top_left[3];
+} nrrt_camera;
+
+/* ======================================================================== */
+/* 2. flat layer: device layout                                             */
+/* ======================================================================== */
+
+/* Node/child reference: bits 31..29 = type, bits 28..0 = index. */
+#define NRRT_REF_TYPE_SHIFT 29u
+#define NRRT_REF_INDEX_MASK 0x1FFFFFFFu
+enum nrrt_ref_type {
+    NRRT_REF_NODE = 0,     /* inner node: index into nodes/boxes        */
+    NRRT_REF_SPHERE = 1,   /* index into sphere arrays                  */
+    NRRT_REF_PLANE = 2,    /* index into plane arrays (quad + triangle) */
+    NRRT_REF_INSTANCE = 3, /* index into instances                      */
+    NRRT_REF_EMPTY = 7     /* BVH::Leaf(None)                           */
+};
+#define NRRT_REF(type, idx) ((((uint32_t)(type)) << NRRT_REF_TYPE_SHIFT) | ((uint32_t)(idx)))
+#define NRRT_REF_TYPE(r) ((r) >> NRRT_REF_TYPE_SHIFT)
+#define NRRT_REF_INDEX(r) ((r) & NRRT_REF_INDEX_MASK)
+#define NRRT_REF_NONE 0xFFFFFFFFu /* == NRRT_REF(EMPTY, all ones) */
+
+/* 64-byte traversal node: both children's boxes in f32 (nearest-rounded from
+ * the f64 boxes; the kernel's certainty margins cover the rounding) and both
+ * child references.  One 128-byte line holds two nodes; loaded as 4 x LDG.128. */
+typedef struct nrrt_node {
+    float lo[2][3]; /* lo[child][axis] */
+    float hi[2][3];
+    uint32_t child[2];
+    uint32_t _pad[2];
+} nrrt_node;
+
+/* Exact f64 box (aabb.rs:6-11) used when the f32 test is inconclusive. */
+typedef struct nrrt_box {
+    double lo[3];
+    double hi[3];
+} nrrt_box;
+
+/* One wrapper of an instance chain, outermost first. */
+enum nrrt_xform_kind { NRRT_XF_TRANSLATE = 0, NRRT_XF_ROTATE = 1, NRRT_XF_SCALE = 2 };
+typedef struct nrrt_xform {
+    uint32_t kind;
+    uint32_t _pad;
+    /* TRANSLATE: to_obj[0..2] = offset.
+     * ROTATE:    to_obj = rotation_mat  (3 columns, DMat3::from_axis_angle(axis,-angle)),
+     *            to_world = rotation_mat_inv (rotate.rs:52-53).
+     * SCALE:     to_obj = scale_matrix_inv columns x,y,z,w (xyz parts, 12 doubles),
+     *            to_world = scale_matrix columns x,y,z,w (scale.rs:48-49). */
+    double to_obj[12];
+    double to_world[12];
+} nrrt_xform;
+
+typedef struct nrrt_instance {
+    uint32_t first_xform; /* index into xforms, outermost wrapper first */
+    uint32_t n_xforms;
+    uint32_t inner;       /* ref of the wrapped object (node / sphere / plane / empty) */
+    uint32_t ordinal;     /* ordinal of this instance leaf inside its owning BVH */
+    nrrt_box inner_box;   /* bbox of `inner` when it is a NODE (tested on entry, object.rs:102) */
+} nrrt_instance;
+
+/* Instance path: the chain of instance leaves from the top-level BVH down to a
+ * nested BVH.  path 0 is the top level (depth 0). */
+#define NRRT_MAX_INSTANCE_DEPTH 4
+typedef struct nrrt_path {
+    uint32_t depth;
+    uint32_t inst[NRRT_MAX_INSTANCE_DEPTH]; /* instance indices, outermost first */
+    uint32_t child_base; /* path id of (this path + instance ordinal k) = child_base + k */
+    uint32_t parent;
+    uint32_t _pad;
+} nrrt_path;
+
+typedef struct nrrt_scene_desc {
+    uint32_t abi_version;
+
+    /* BVH */
+    uint32_t n_nodes;
+    const nrrt_node* nodes;      /* [n_nodes]                                   */
+    const nrrt_box* child_boxes; /* [2*n_nodes] exact box of child c of node i at 2*i+c */
+    uint32_t root;               /* ref of Scene.objects                        */
+    nrrt_box root_box;           /* its bbox when root is a NODE                */
+
+    /* spheres (SoA) */
+    uint32_t n_spheres;
+    const double* sphere_center; /* [n][3] */
+    const double* sphere_radius; /* [n]    */
+    const uint32_t* sphere_material;
+    const uint32_t* sphere_order;  /* DFS leaf order (tie-break, object.rs:110-114) */
+    const uint32_t* sphere_object; /* graph object index (reported in nrrt_hit.object) */
+
+    /* planes (SoA): p,u,v + the derived normal,d,w exactly as PlaneBuilder::build */
+    uint32_t n_planes;
+    const double* plane_p;      /* [n][3] */
+    const double* plane_u;      /* [n][3] */
+    const double* plane_v;      /* [n][3] */
+    const double* plane_normal; /* [n][3] */
+    const double* plane_w;      /* [n][3] */
+    const double* plane_d;      /* [n]    */
+    const uint32_t* plane_material; /* bit 31 set = Triangle, else Quad */
+    const uint32_t* plane_order;
+    const uint32_t* plane_object;
+
+    /* instances */
+    uint32_t n_instances;
+    const nrrt_instance* instances;
+    const uint32_t* instance_order;
+    uint32_t n_xforms;
+    const nrrt_xform* xforms;
+    uint32_t n_paths;
+    const nrrt_path* paths;
+
+    /* shading tables */
+    uint32_t n_materials;
+    const nrrt_material* materials;
+    uint32_t n_textures;
+    const nrrt_texture* textures;
+    uint32_t n_images;
+    const nrrt_image* images;
+
+    uint32_t max_stack; /* worst-case traversal stack entries (validated by the host) */
+} nrrt_scene_desc;
+
+#define NRRT_PLANE_TRIANGLE_BIT 0x80000000u
+
+/* ---- host side: reference's BVH build + flatten (no GPU needed) -------- */
+typedef struct nrrt_host_scene nrrt_host_scene;
+
+/* Builds the object graph, runs BVH::from exactly as the reference does and
+ * flattens it.  `graph` is borrowed for the call only.  Returns NULL on error
+ * (message via nrrt_host_last_error). */
+nrrt_host_scene* nrrt_host_build(const nrrt_graph_desc* graph);
+const nrrt_scene_desc* nrrt_host_scene_desc(const nrrt_host_scene* scene);
+void nrrt_host_free(nrrt_host_scene* scene);
+const char* nrrt_host_last_error(void);
+
+/* CameraBuilder::build (camera.rs:94-159). */
+int nrrt_host_camera_build(const nrrt_camera_config* config, nrrt_camera* out);
+
+/* ---- device side -------------------------------------------------------- */
+typedef struct nrrt_ctx nrrt_ctx;
+
+/* One context per GPU (one process per GPU under torch.distributed). */
+int nrrt_create(int device, nrrt_ctx** out);
+void nrrt_destroy(nrrt_ctx* ctx);
+const char* nrrt_last_error(const nrrt_ctx* ctx); /* ctx may be NULL: last create error */
+
+/* Launch on this CUDA stream (a cudaStream_t passed as void*); default 0. */
+int nrrt_set_stream(nrrt_ctx* ctx, void* cuda_stream);
+
+/* Copies the flat scene to HBM (host pointers borrowed for the call only). */
+int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* scene);
+
+/* Closest-hit query result = HitRecord (hitable.rs:15-22) + ids. */
+typedef struct nrrt_hit {
+    double t;          /* +inf on miss */
+    double point[3];
+    double normal[3];
+    double uv[2];
+    uint32_t prim;     /* winning primitive ref (NRRT_REF_NONE on miss) */
+    uint32_t path;     /* instance path id */
+    uint32_t material;
+    uint32_t front_face;
+    uint32_t object;   /* graph object index of the winning primitive (0xFFFFFFFF on miss) */
+    uint32_t _pad;
+} nrrt_hit;
+
+enum {
+    NRRT_TRACE_ORDERED = 0,    /* near-first traversal with conservative t-shrinking (render path) */
+    NRRT_TRACE_VISIT_ALL = 1,  /* visit exactly the reference's node set (no shrinking)            */
+    NRRT_TRACE_HOST_BUFFERS = 0,
+    NRRT_TRACE_DEVICE_BUFFERS = 2
+};
+
+typedef struct nrrt_trace_stats {
+    uint64_t node_visits;   /* inner nodes fetched                 */
+    uint64_t box_exact;     /* f32-inconclusive box tests redone in f64 */
+    uint64_t prim_tests;    /* exact primitive tests               */
+    double kernel_ms;       /* CUDA-event time of the kernel       */
+} nrrt_trace_stats;
+
+/* BVH::hit (object.rs:89-121) for n rays: rays = n x {ox,oy,oz,dx,dy,dz}. */
+int nrrt_trace_rays(nrrt_ctx* ctx, const double* rays, uint64_t n, double tmin, double tmax,
+                    uint32_t flags, nrrt_hit* out, nrrt_trace_stats* stats /* may be NULL */);
+
+enum nrrt_render_mode {
+    NRRT_MODE_WAVEFRONT = 0, /* raygen / extend / shade+compact kernels over ray queues */
+    NRRT_MODE_MEGAKERNEL = 1 /* one persistent kernel, per-thread path loop             */
+};
+
+typedef struct nrrt_render_opts {
+    uint64_t seed;        /* Philox key; the reference seeds ChaCha8 with 0 (camera.rs:318) */
+    uint32_t mode;        /* nrrt_render_mode */
+    uint32_t rank, world; /* tile partition: this context renders row-blocks b with b % world == rank */
+    uint32_t rows_per_block; /* height of one row-block (0 -> default 8) */
+    uint32_t max_slots;   /* wavefront: path slots in flight (0 -> auto) */
+    uint32_t flags;       /* NRRT_RENDER_* */
+} nrrt_render_opts;
+
+enum {
+    NRRT_RENDER_OUT_HOST = 0,
+    NRRT_RENDER_OUT_DEVICE = 1 /* out_rgb is a device pointer */
+};
+
+typedef struct nrrt_render_stats {
+    uint64_t paths;        /* pixel samples traced by this context             */
+    uint64_t segments;     /* closest-hit queries issued (camera.rs:280)       */
+    uint64_t launches;     /* kernels launched                                 */
+    double device_ms;      /* CUDA-event time, first launch -> last launch     */
+    double extend_ms;      /* share of device_ms in the traverse/intersect kernel (wavefront) */
+    uint64_t extend_launches;
+    uint32_t pixels;       /* pixels owned by this rank                        */
+    uint32_t _pad;
+} nrrt_render_stats;
+
+typedef void (*nrrt_progress_fn)(uint64_t pixels_done, uint64_t pixels_total, void* user);
+
+/* Camera::render (camera.rs:302-343).  out_rgb: width*height*3 f32, row-major
+ * interleaved RGB, linear radiance (no gamma, no clamp).  With world > 1 only
+ * the rows owned by `rank` are written (others left untouched). */
+int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* camera, const nrrt_render_opts* opts,
+                float* out_rgb, nrrt_progress_fn progress, void* user, nrrt_render_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRRT_H */

@@ -198,20 +198,13 @@ typedef struct nrrt_instance {
     uint32_t first_xform; /* index into xforms, outermost wrapper first */
     uint32_t n_xforms;
     uint32_t inner;       /* ref of the wrapped object (node / sphere / plane / empty) */
-    uint32_t ordinal;     /* ordinal of this instance leaf inside its owning BVH */
+    uint32_t _pad;
     nrrt_box inner_box;   /* bbox of `inner` when it is a NODE (tested on entry, object.rs:102) */
 } nrrt_instance;
 
-/* Instance path: the chain of instance leaves from the top-level BVH down to a
- * nested BVH.  path 0 is the top level (depth 0). */
+/* Instances nest (a wrapped group may contain wrappers again); a hit carries the
+ * chain of instance indices from the top-level BVH down to the primitive. */
 #define NRRT_MAX_INSTANCE_DEPTH 4
-typedef struct nrrt_path {
-    uint32_t depth;
-    uint32_t inst[NRRT_MAX_INSTANCE_DEPTH]; /* instance indices, outermost first */
-    uint32_t child_base; /* path id of (this path + instance ordinal k) = child_base + k */
-    uint32_t parent;
-    uint32_t _pad;
-} nrrt_path;
 
 typedef struct nrrt_scene_desc {
     uint32_t abi_version;
@@ -249,8 +242,6 @@ typedef struct nrrt_scene_desc {
     const uint32_t* instance_order;
     uint32_t n_xforms;
     const nrrt_xform* xforms;
-    uint32_t n_paths;
-    const nrrt_path* paths;
 
     /* shading tables */
     uint32_t n_materials;
@@ -300,10 +291,11 @@ typedef struct nrrt_hit {
     double normal[3];
     double uv[2];
     uint32_t prim;     /* winning primitive ref (NRRT_REF_NONE on miss) */
-    uint32_t path;     /* instance path id */
     uint32_t material;
     uint32_t front_face;
     uint32_t object;   /* graph object index of the winning primitive (0xFFFFFFFF on miss) */
+    uint32_t depth;    /* number of instance levels above the primitive */
+    uint32_t inst[NRRT_MAX_INSTANCE_DEPTH]; /* instance indices, outermost first */
     uint32_t _pad;
 } nrrt_hit;
 
@@ -362,6 +354,11 @@ typedef void (*nrrt_progress_fn)(uint64_t pixels_done, uint64_t pixels_total, vo
  * the rows owned by `rank` are written (others left untouched). */
 int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* camera, const nrrt_render_opts* opts,
                 float* out_rgb, nrrt_progress_fn progress, void* user, nrrt_render_stats* stats);
+
+/* sizeof() of the ABI structs as compiled (which = 0..15 in header order: object, material, texture,
+ * image, graph_desc, camera_config, camera, node, box, xform, instance, scene_desc, hit, trace_stats,
+ * render_opts, render_stats) so a binding can verify its mirror of this header. */
+size_t nrrt_abi_sizeof(int which);
 
 #ifdef __cplusplus
 }

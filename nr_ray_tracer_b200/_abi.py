@@ -82,11 +82,7 @@ class Xform(C.Structure):
 
 
 class Instance(C.Structure):
-    _fields_ = [("first_xform", u32), ("n_xforms", u32), ("inner", u32), ("ordinal", u32), ("inner_box", Box)]
-
-
-class Path(C.Structure):
-    _fields_ = [("depth", u32), ("inst", u32 * MAX_INSTANCE_DEPTH), ("child_base", u32), ("parent", u32), ("_pad", u32)]
+    _fields_ = [("first_xform", u32), ("n_xforms", u32), ("inner", u32), ("_pad", u32), ("inner_box", Box)]
 
 
 class SceneDesc(C.Structure):
@@ -101,7 +97,6 @@ class SceneDesc(C.Structure):
         ("plane_material", C.POINTER(u32)), ("plane_order", C.POINTER(u32)), ("plane_object", C.POINTER(u32)),
         ("n_instances", u32), ("instances", C.POINTER(Instance)), ("instance_order", C.POINTER(u32)),
         ("n_xforms", u32), ("xforms", C.POINTER(Xform)),
-        ("n_paths", u32), ("paths", C.POINTER(Path)),
         ("n_materials", u32), ("materials", C.POINTER(Material)),
         ("n_textures", u32), ("textures", C.POINTER(Texture)),
         ("n_images", u32), ("images", C.POINTER(Image)),
@@ -111,7 +106,8 @@ class SceneDesc(C.Structure):
 
 class Hit(C.Structure):
     _fields_ = [("t", f64), ("point", f64 * 3), ("normal", f64 * 3), ("uv", f64 * 2),
-                ("prim", u32), ("path", u32), ("material", u32), ("front_face", u32), ("object", u32), ("_pad", u32)]
+                ("prim", u32), ("material", u32), ("front_face", u32), ("object", u32), ("depth", u32),
+                ("inst", u32 * MAX_INSTANCE_DEPTH), ("_pad", u32)]
 
 
 class TraceStats(C.Structure):
@@ -134,6 +130,6 @@ PROGRESS_FN = C.CFUNCTYPE(None, u64, u64, C.c_void_p)
 import numpy as _np  # noqa: E402
 
 HIT_DTYPE = _np.dtype([("t", "<f8"), ("point", "<f8", (3,)), ("normal", "<f8", (3,)), ("uv", "<f8", (2,)),
-                       ("prim", "<u4"), ("path", "<u4"), ("material", "<u4"), ("front_face", "<u4"),
-                       ("object", "<u4"), ("_pad", "<u4")])
+                       ("prim", "<u4"), ("material", "<u4"), ("front_face", "<u4"), ("object", "<u4"),
+                       ("depth", "<u4"), ("inst", "<u4", (MAX_INSTANCE_DEPTH,)), ("_pad", "<u4")])
 assert HIT_DTYPE.itemsize == C.sizeof(Hit)

@@ -1,0 +1,207 @@
+"""Python host mirror of the reference's render API over the C ABI (include/nrrt.h).
+
+Reference interface mirrored here (names and meaning kept):
+  Scene { camera, objects }  / Scene::render(progress) -> Rgb32FImage   ray-tracer-lib/src/scene.rs:7-18
+  Camera::render(hitable, progress)                                      ray-tracer-lib/src/camera.rs:302-343
+  SceneConfig::try_load_scene / try_build                                ray-tracer/src/scene_config.rs:475-496
+
+Everything that computes runs in libnrrt_b200.so (CUDA, sm_100a).  There is no CPU fallback: if the
+library or a GPU is missing, calls raise NrrtError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import _abi as A
+from .scene_config import CameraConfig, SceneGraph, load_scene
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnrrt_b200.so")
+_lib = None
+
+
+class NrrtError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"nrrt error {code}: {msg}")
+        self.code = code
+
+
+def lib() -> C.CDLL:
+    """Loads the native library; never falls back to anything else."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise NrrtError(A.ERR_NO_DEVICE, f"{_LIB_PATH} is not built (run `python -m nr_ray_tracer_b200.build`); "
+                                             "there is no CPU fallback")
+        L = C.CDLL(_LIB_PATH)
+        L.nrrt_host_build.restype = C.c_void_p
+        L.nrrt_host_build.argtypes = [C.POINTER(A.GraphDesc)]
+        L.nrrt_host_scene_desc.restype = C.POINTER(A.SceneDesc)
+        L.nrrt_host_scene_desc.argtypes = [C.c_void_p]
+        L.nrrt_host_free.argtypes = [C.c_void_p]
+        L.nrrt_host_last_error.restype = C.c_char_p
+        L.nrrt_host_camera_build.argtypes = [C.POINTER(A.CameraConfig), C.POINTER(A.Camera)]
+        L.nrrt_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.nrrt_destroy.argtypes = [C.c_void_p]
+        L.nrrt_last_error.restype = C.c_char_p
+        L.nrrt_last_error.argtypes = [C.c_void_p]
+        L.nrrt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.nrrt_scene_upload.argtypes = [C.c_void_p, C.POINTER(A.SceneDesc)]
+        L.nrrt_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_uint32,
+                                      C.c_void_p, C.POINTER(A.TraceStats)]
+        L.nrrt_render.argtypes = [C.c_void_p, C.POINTER(A.Camera), C.POINTER(A.RenderOpts), C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.POINTER(A.RenderStats)]
+        L.nrrt_abi_sizeof.restype = C.c_size_t
+        L.nrrt_abi_sizeof.argtypes = [C.c_int]
+        _lib = L
+    return _lib
+
+
+ABI_STRUCTS = [A.Object, A.Material, A.Texture, A.Image, A.GraphDesc, A.CameraConfig, A.Camera, A.Node, A.Box,
+               A.Xform, A.Instance, A.SceneDesc, A.Hit, A.TraceStats, A.RenderOpts, A.RenderStats]
+
+
+def camera_build(cfg: A.CameraConfig) -> A.Camera:
+    """CameraBuilder::build (camera.rs:94-159) on the host."""
+    cam = A.Camera()
+    rc = lib().nrrt_host_camera_build(C.byref(cfg), C.byref(cam))
+    if rc != 0:
+        raise NrrtError(rc, "nrrt_host_camera_build: bad configuration")
+    return cam
+
+
+class HostScene:
+    """Object graph -> reference BVH (objects/object.rs:41-73) -> flat device layout.  Pure host code."""
+
+    def __init__(self, graph: SceneGraph):
+        self._holder = graph.to_desc()
+        self._h = lib().nrrt_host_build(self._holder.ptr())
+        if not self._h:
+            raise NrrtError(A.ERR_INVALID, lib().nrrt_host_last_error().decode())
+        self.desc = lib().nrrt_host_scene_desc(self._h).contents
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().nrrt_host_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # numpy views for tests / inspection
+    def nodes(self) -> np.ndarray:
+        n = self.desc.n_nodes
+        dt = np.dtype([("lo", "<f4", (2, 3)), ("hi", "<f4", (2, 3)), ("child", "<u4", (2,)), ("_pad", "<u4", (2,))])
+        if n == 0:
+            return np.zeros(0, dtype=dt)
+        return np.ctypeslib.as_array(C.cast(self.desc.nodes, C.POINTER(C.c_uint8)), shape=(n * 64,)).view(dt).copy()
+
+    def child_boxes(self) -> np.ndarray:
+        n = self.desc.n_nodes
+        if n == 0:
+            return np.zeros((0, 2, 2, 3))
+        a = np.ctypeslib.as_array(C.cast(self.desc.child_boxes, C.POINTER(C.c_double)), shape=(n, 2, 2, 3))
+        return a.copy()
+
+
+class Context:
+    """One GPU context (one process per GPU).  Owns all device memory."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        rc = lib().nrrt_create(device, C.byref(h))
+        if rc != 0:
+            raise NrrtError(rc, lib().nrrt_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().nrrt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise NrrtError(rc, lib().nrrt_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream: int):
+        self._check(lib().nrrt_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def upload(self, scene: HostScene):
+        self._check(lib().nrrt_scene_upload(self._h, C.byref(scene.desc)))
+
+    def trace_rays(self, rays: np.ndarray, tmin: float = 0.001, tmax: float = float("inf"), visit_all: bool = False,
+                   want_stats: bool = True):
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros(rays.shape[0], dtype=A.HIT_DTYPE)
+        st = A.TraceStats()
+        flags = A.TRACE_VISIT_ALL if visit_all else A.TRACE_ORDERED
+        self._check(lib().nrrt_trace_rays(self._h, rays.ctypes.data, rays.shape[0], tmin, tmax, flags, out.ctypes.data,
+                                          C.byref(st) if want_stats else None))
+        return out, {"node_visits": st.node_visits, "box_exact": st.box_exact, "prim_tests": st.prim_tests,
+                     "kernel_ms": st.kernel_ms}
+
+    def trace_rays_device(self, rays_ptr: int, n: int, out_ptr: int, tmin: float = 0.001, tmax: float = float("inf"),
+                          visit_all: bool = False):
+        """rays_ptr / out_ptr are device pointers (n x 6 f64, n x nrrt_hit)."""
+        st = A.TraceStats()
+        flags = (A.TRACE_VISIT_ALL if visit_all else A.TRACE_ORDERED) | A.TRACE_DEVICE_BUFFERS
+        self._check(lib().nrrt_trace_rays(self._h, C.c_void_p(rays_ptr), n, tmin, tmax, flags, C.c_void_p(out_ptr),
+                                          C.byref(st)))
+        return {"node_visits": st.node_visits, "box_exact": st.box_exact, "prim_tests": st.prim_tests,
+                "kernel_ms": st.kernel_ms}
+
+    def render(self, cam: A.Camera, out: Optional[np.ndarray] = None, seed: int = 0, mode: int = A.MODE_MEGAKERNEL,
+               rank: int = 0, world: int = 1, rows_per_block: int = 0, max_slots: int = 0,
+               out_device_ptr: Optional[int] = None, progress: Optional[Callable[[int, int], None]] = None):
+        """Camera::render.  Returns (image (H, W, 3) float32 or None for device output, stats dict)."""
+        opts = A.RenderOpts(seed=seed, mode=mode, rank=rank, world=world, rows_per_block=rows_per_block,
+                            max_slots=max_slots, flags=A.RENDER_OUT_DEVICE if out_device_ptr is not None else 0)
+        st = A.RenderStats()
+        cb = A.PROGRESS_FN(lambda done, total, user: progress(done, total)) if progress else None
+        if out_device_ptr is not None:
+            ptr = C.c_void_p(out_device_ptr)
+        else:
+            if out is None:
+                out = np.zeros((cam.height, cam.width, 3), dtype=np.float32)
+            assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == cam.height * cam.width * 3
+            ptr = C.c_void_p(out.ctypes.data)
+        self._check(lib().nrrt_render(self._h, C.byref(cam), C.byref(opts), ptr, C.cast(cb, C.c_void_p) if cb else None,
+                                      None, C.byref(st)))
+        stats = {k: getattr(st, k) for k in ("paths", "segments", "launches", "device_ms", "extend_ms",
+                                             "extend_launches", "pixels")}
+        return (None if out_device_ptr is not None else out), stats
+
+
+class Scene:
+    """Drop-in for the reference's Scene (scene.rs:7-18): `Scene.load(path).render()`."""
+
+    def __init__(self, graph: SceneGraph, device: int = 0, ctx: Optional[Context] = None):
+        self.graph = graph
+        self.camera = camera_build(graph.camera.to_builder_config())
+        self.host = HostScene(graph)
+        self.ctx = ctx or Context(device)
+        self.ctx.upload(self.host)
+
+    @classmethod
+    def load(cls, path: str, camera_override: Optional[CameraConfig] = None, base_dir: Optional[str] = None,
+             device: int = 0, ctx: Optional[Context] = None) -> "Scene":
+        """SceneConfig::try_load_scene + camera merge + try_build (render.rs:104-111)."""
+        return cls(load_scene(path, base_dir=base_dir, camera_override=camera_override), device=device, ctx=ctx)
+
+    def render(self, progress: Optional[Callable[[int, int], None]] = None, **kw) -> np.ndarray:
+        """Scene::render -> linear f32 RGB image (H, W, 3), no gamma, no clamp."""
+        img, self.last_stats = self.ctx.render(self.camera, progress=progress, **kw)
+        return img

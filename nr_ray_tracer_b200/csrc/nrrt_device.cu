@@ -1,0 +1,905 @@
+// nrrt_device.cu — CUDA kernels (sm_100a) and the device half of the C ABI (include/nrrt.h).
+//
+// Kernels
+//   k_trace_rays      BVH::hit for a batch of fixed rays (known-answer tests, traversal microbenchmark)
+//   k_render_mega     persistent per-thread path loop: camera ray -> (closest hit -> shade/scatter)* with
+//                     in-lane path regeneration; state lives in registers
+//   k_wf_init/extend/shade   wavefront variant: ray-gen, traverse/intersect and shade/scatter(+regeneration,
+//                     +warp-ballot queue compaction) as separate kernels over SoA path state in HBM
+//   k_resolve         per-pixel sample accumulation -> f32 RGB (camera.rs:329-337)
+// There is no CPU fallback: every entry point fails with NRRT_ERR_NO_DEVICE / NRRT_ERR_CUDA when the GPU
+// is unavailable.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_device.cuh"
+
+#define NRRT_BLOCK 128
+
+// =========================================================================== kernels
+struct RenderParams {
+    uint2 key;               // Philox key
+    uint32_t n_owned_pixels; // pixels rendered by this context
+    uint32_t lanes;          // sample lanes per pixel: lane l renders samples l, l+lanes, ...
+    uint32_t n_work;         // n_owned_pixels * lanes
+    uint32_t rank, world, rows_per_block;
+};
+
+// owned pixel index -> (x, y): rank owns row-blocks b with b % world == rank
+__device__ __forceinline__ void owned_pixel(const nrrt_camera& cam, const RenderParams& P, uint32_t po, uint32_t& x,
+                                            uint32_t& y) {
+    uint32_t W = cam.width;
+    uint32_t j = po / W;
+    x = po - j * W;
+    uint32_t b = j / P.rows_per_block, r = j - b * P.rows_per_block;
+    y = (b * P.world + P.rank) * P.rows_per_block + r;
+}
+
+template <bool VISIT_ALL, bool COUNT>
+__global__ void __launch_bounds__(NRRT_BLOCK)
+k_trace_rays(const __grid_constant__ DevScene S, const double* __restrict__ rays, uint64_t n, double tmin, double tmax,
+             nrrt_hit* __restrict__ out, unsigned long long* __restrict__ counters) {
+    extern __shared__ uint32_t s_stack[];
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d3 o = ld3(rays + 6 * i), d = ld3(rays + 6 * i + 3);
+    HitId h;
+    TraceCounters tc{0, 0, 0};
+    trace_closest<VISIT_ALL, COUNT>(S, o, d, tmin, tmax, s_stack + threadIdx.x, blockDim.x, h, &tc);
+    nrrt_hit r;
+    r.t = h.t;
+    r.prim = h.prim;
+    r.depth = h.depth;
+#pragma unroll
+    for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) r.inst[k] = h.inst[k];
+    r._pad = 0;
+    if (h.prim != NRRT_REF_NONE) {
+        HitRec rec;
+        resolve_hit(S, h, o, d, true, rec);
+        r.point[0] = rec.point.x, r.point[1] = rec.point.y, r.point[2] = rec.point.z;
+        r.normal[0] = rec.normal.x, r.normal[1] = rec.normal.y, r.normal[2] = rec.normal.z;
+        r.uv[0] = rec.u, r.uv[1] = rec.v;
+        r.material = rec.material;
+        r.front_face = rec.front_face ? 1u : 0u;
+        uint32_t ix = NRRT_REF_INDEX(h.prim);
+        r.object = NRRT_REF_TYPE(h.prim) == NRRT_REF_SPHERE ? S.sphere_object[ix] : S.plane_object[ix];
+    } else {
+        r.point[0] = r.point[1] = r.point[2] = 0.0;
+        r.normal[0] = r.normal[1] = r.normal[2] = 0.0;
+        r.uv[0] = r.uv[1] = 0.0;
+        r.material = 0xFFFFFFFFu;
+        r.front_face = 0;
+        r.object = 0xFFFFFFFFu;
+    }
+    out[i] = r;
+    if (COUNT) {
+        atomicAdd(&counters[0], (unsigned long long)tc.nodes);
+        atomicAdd(&counters[1], (unsigned long long)tc.exact);
+        atomicAdd(&counters[2], (unsigned long long)tc.prims);
+    }
+}
+
+// One step of Camera::get_ray_color (camera.rs:269-300) in iterative form:  L += T*emitted; T *= color.
+// Returns true while the path is alive.
+__device__ __forceinline__ bool path_step(const DevScene& S, const nrrt_camera& cam, const HitId& h, const Sampler& smp,
+                                          d3& o, d3& d, d3& T, d3& L, uint32_t& bounce) {
+    if (h.prim == NRRT_REF_NONE) {  // camera.rs:298
+        L = add3(L, mul3(T, ld3(cam.background)));
+        return false;
+    }
+    HitRec rec;
+    uint32_t mat = NRRT_REF_TYPE(h.prim) == NRRT_REF_SPHERE ? S.sphere_material[NRRT_REF_INDEX(h.prim)]
+                                                            : (S.plane_material[NRRT_REF_INDEX(h.prim)] & ~NRRT_PLANE_TRIANGLE_BIT);
+    resolve_hit(S, h, o, d, (S.material_flags[mat] & 1u) != 0, rec);
+    d3 emitted, atten, nd;
+    bool cont = shade_hit(S, rec, d, bounce == 0, smp, bounce + 1, emitted, atten, nd);
+    L = add3(L, mul3(T, emitted));
+    if (!cont) return false;
+    T = mul3(T, atten);
+    o = rec.point;
+    d = nd;
+    ++bounce;
+    return bounce < cam.ray_max_bounces;  // camera.rs:276-278
+}
+
+__global__ void __launch_bounds__(NRRT_BLOCK)
+k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_camera cam,
+              const __grid_constant__ RenderParams P, double* __restrict__ acc, unsigned long long* __restrict__ counters) {
+    extern __shared__ uint32_t s_stack[];
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long segs = 0, paths = 0;
+    if (w < P.n_work) {
+        uint32_t lane = w / P.n_owned_pixels, po = w - lane * P.n_owned_pixels;
+        uint32_t x, y;
+        owned_pixel(cam, P, po, x, y);
+        Sampler smp{P.key, y * cam.width + x, lane};
+        const uint32_t spp = cam.samples_per_pixel;
+        d3 sum = mk3(0.0, 0.0, 0.0);
+        d3 o, d, T, L;
+        uint32_t bounce = 0;
+        bool alive = false;
+        for (;;) {
+            if (!alive) {  // regenerate: next sample of this lane
+                if (smp.sample >= spp) break;
+                camera_ray(cam, x, y, smp, o, d);
+                T = mk3(1.0, 1.0, 1.0);
+                L = mk3(0.0, 0.0, 0.0);
+                bounce = 0;
+                alive = true;
+                ++paths;
+            }
+            HitId h;
+            trace_closest<false, false>(S, o, d, 0.001, NRRT_INF, s_stack + threadIdx.x, blockDim.x, h, nullptr);
+            ++segs;
+            alive = path_step(S, cam, h, smp, o, d, T, L, bounce);
+            if (!alive) {
+                sum = add3(sum, L);
+                smp.sample += P.lanes;
+            }
+        }
+        size_t base = (size_t)w * 3;
+        acc[base] = sum.x, acc[base + 1] = sum.y, acc[base + 2] = sum.z;
+    }
+    // block-level reduction of the counters
+    __shared__ unsigned long long s_cnt[2];
+    if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = 0;
+    __syncthreads();
+    for (int off = 16; off; off >>= 1) {
+        segs += __shfl_down_sync(0xffffffffu, segs, off);
+        paths += __shfl_down_sync(0xffffffffu, paths, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_cnt[0], segs);
+        atomicAdd(&s_cnt[1], paths);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&counters[0], s_cnt[0]);
+        atomicAdd(&counters[1], s_cnt[1]);
+    }
+}
+
+// sum the lanes of every owned pixel in lane order, divide by spp, cast to f32 (camera.rs:331-337)
+__global__ void k_resolve(const __grid_constant__ nrrt_camera cam, const __grid_constant__ RenderParams P,
+                          const double* __restrict__ acc, float* __restrict__ out) {
+    uint32_t po = blockIdx.x * blockDim.x + threadIdx.x;
+    if (po >= P.n_owned_pixels) return;
+    d3 s = mk3(0.0, 0.0, 0.0);
+    for (uint32_t l = 0; l < P.lanes; ++l) {
+        size_t b = ((size_t)l * P.n_owned_pixels + po) * 3;
+        s = add3(s, mk3(acc[b], acc[b + 1], acc[b + 2]));
+    }
+    d3 c = div3(s, (double)cam.samples_per_pixel);
+    uint32_t x, y;
+    owned_pixel(cam, P, po, x, y);
+    size_t ob = ((size_t)y * cam.width + x) * 3;
+    out[ob] = (float)c.x, out[ob + 1] = (float)c.y, out[ob + 2] = (float)c.z;
+}
+
+// ------------------------------------------------------------------ wavefront
+// SoA path state, one slot per (lane, owned pixel).  All arrays have n_work entries per component.
+struct WfState {
+    double* ray;    // [6][n]: ox oy oz dx dy dz
+    double* T;      // [3][n]
+    double* L;      // [3][n]
+    double* acc;    // [n][3] (same layout k_resolve reads)
+    uint32_t* sample;  // [n] current sample index
+    uint32_t* bounce;  // [n]
+    double* hit_t;     // [n]
+    uint32_t* hit_prim;   // [n]
+    uint32_t* hit_inst;   // [1 + MAX_DEPTH][n]: depth, inst[0..]
+    uint32_t* queue[2];   // [n] slot indices
+    uint32_t* count;      // [2] queue lengths
+    unsigned long long* counters;  // [0]=segments [1]=paths
+};
+
+__global__ void __launch_bounds__(NRRT_BLOCK)
+k_wf_init(const __grid_constant__ nrrt_camera cam, const __grid_constant__ RenderParams P,
+          const __grid_constant__ WfState W) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w == 0) {
+        W.count[0] = P.n_work;
+        W.count[1] = 0;
+        W.counters[1] += P.n_work;
+    }
+    if (w >= P.n_work) return;
+    uint32_t n = P.n_work;
+    uint32_t lane = w / P.n_owned_pixels, po = w - lane * P.n_owned_pixels;
+    uint32_t x, y;
+    owned_pixel(cam, P, po, x, y);
+    Sampler smp{P.key, y * cam.width + x, lane};
+    d3 o, d;
+    camera_ray(cam, x, y, smp, o, d);
+    W.ray[0 * (size_t)n + w] = o.x, W.ray[1 * (size_t)n + w] = o.y, W.ray[2 * (size_t)n + w] = o.z;
+    W.ray[3 * (size_t)n + w] = d.x, W.ray[4 * (size_t)n + w] = d.y, W.ray[5 * (size_t)n + w] = d.z;
+    for (int c = 0; c < 3; ++c) {
+        W.T[c * (size_t)n + w] = 1.0;
+        W.L[c * (size_t)n + w] = 0.0;
+        W.acc[(size_t)w * 3 + c] = 0.0;
+    }
+    W.sample[w] = lane;
+    W.bounce[w] = 0;
+    W.queue[0][w] = w;
+}
+
+// traverse / intersect: closest hit for every queued ray
+__global__ void __launch_bounds__(NRRT_BLOCK)
+k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState W, uint32_t n, uint32_t qin) {
+    extern __shared__ uint32_t s_stack[];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n_in = W.count[qin];
+    if (i == 0) W.count[qin ^ 1] = 0;  // the other queue is filled by the next shade pass
+    if (i >= n_in) return;
+    uint32_t slot = W.queue[qin][i];
+    d3 o = mk3(W.ray[slot], W.ray[(size_t)n + slot], W.ray[2 * (size_t)n + slot]);
+    d3 d = mk3(W.ray[3 * (size_t)n + slot], W.ray[4 * (size_t)n + slot], W.ray[5 * (size_t)n + slot]);
+    HitId h;
+    trace_closest<false, false>(S, o, d, 0.001, NRRT_INF, s_stack + threadIdx.x, blockDim.x, h, nullptr);
+    W.hit_t[slot] = h.t;
+    W.hit_prim[slot] = h.prim;
+    W.hit_inst[slot] = h.depth;
+    for (uint32_t l = 0; l < h.depth; ++l) W.hit_inst[(size_t)(1 + l) * n + slot] = h.inst[l];
+}
+
+// shade / scatter, path regeneration, warp-ballot compaction of the survivors into the other queue
+__global__ void __launch_bounds__(NRRT_BLOCK)
+k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_camera cam,
+           const __grid_constant__ RenderParams P, const __grid_constant__ WfState W, uint32_t qin) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = P.n_work;
+    uint32_t n_in = W.count[qin];
+    if (i == 0) W.counters[0] += n_in;  // one closest-hit query per queued ray
+    bool survive = false;
+    uint32_t slot = 0;
+    if (i < n_in) {
+        slot = W.queue[qin][i];
+        d3 o = mk3(W.ray[slot], W.ray[(size_t)n + slot], W.ray[2 * (size_t)n + slot]);
+        d3 d = mk3(W.ray[3 * (size_t)n + slot], W.ray[4 * (size_t)n + slot], W.ray[5 * (size_t)n + slot]);
+        d3 T = mk3(W.T[slot], W.T[(size_t)n + slot], W.T[2 * (size_t)n + slot]);
+        d3 L = mk3(W.L[slot], W.L[(size_t)n + slot], W.L[2 * (size_t)n + slot]);
+        uint32_t bounce = W.bounce[slot];
+        uint32_t lane = slot / P.n_owned_pixels, po = slot - lane * P.n_owned_pixels;
+        uint32_t x, y;
+        owned_pixel(cam, P, po, x, y);
+        Sampler smp{P.key, y * cam.width + x, W.sample[slot]};
+        HitId h;
+        h.t = W.hit_t[slot];
+        h.prim = W.hit_prim[slot];
+        h.depth = (h.prim == NRRT_REF_NONE) ? 0u : W.hit_inst[slot];
+#pragma unroll
+        for (uint32_t l = 0; l < NRRT_MAX_INSTANCE_DEPTH; ++l)
+            h.inst[l] = (l < h.depth) ? W.hit_inst[(size_t)(1 + l) * n + slot] : 0u;
+        bool alive = path_step(S, cam, h, smp, o, d, T, L, bounce);
+        if (!alive) {  // path finished: accumulate, then regenerate the lane's next sample in place
+            size_t ab = (size_t)slot * 3;
+            W.acc[ab] = xadd(W.acc[ab], L.x);
+            W.acc[ab + 1] = xadd(W.acc[ab + 1], L.y);
+            W.acc[ab + 2] = xadd(W.acc[ab + 2], L.z);
+            smp.sample += P.lanes;
+            if (smp.sample < cam.samples_per_pixel) {
+                camera_ray(cam, x, y, smp, o, d);
+                T = mk3(1.0, 1.0, 1.0);
+                L = mk3(0.0, 0.0, 0.0);
+                bounce = 0;
+                alive = true;
+                W.sample[slot] = smp.sample;
+                atomicAdd(&W.counters[1], 1ull);
+            }
+        }
+        if (alive) {
+            W.ray[slot] = o.x, W.ray[(size_t)n + slot] = o.y, W.ray[2 * (size_t)n + slot] = o.z;
+            W.ray[3 * (size_t)n + slot] = d.x, W.ray[4 * (size_t)n + slot] = d.y, W.ray[5 * (size_t)n + slot] = d.z;
+            W.T[slot] = T.x, W.T[(size_t)n + slot] = T.y, W.T[2 * (size_t)n + slot] = T.z;
+            W.L[slot] = L.x, W.L[(size_t)n + slot] = L.y, W.L[2 * (size_t)n + slot] = L.z;
+            W.bounce[slot] = bounce;
+        }
+        survive = alive;
+    }
+    // warp-aggregated compaction
+    unsigned ballot = __ballot_sync(0xffffffffu, survive);
+    if (ballot) {
+        uint32_t lane_id = threadIdx.x & 31u;
+        uint32_t base = 0;
+        if (lane_id == 0) base = atomicAdd(&W.count[qin ^ 1], (uint32_t)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (survive) W.queue[qin ^ 1][base + __popc(ballot & ((1u << lane_id) - 1u))] = slot;
+    }
+}
+
+// =========================================================================== host side of the ABI
+static std::string g_create_error;
+
+struct nrrt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool has_scene = false;
+    DevScene dev{};
+    uint32_t max_stack = 0;
+    std::vector<void*> scene_allocs;
+    std::vector<cudaTextureObject_t> tex_objs;
+    std::vector<cudaArray_t> tex_arrays;
+    // scratch
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    unsigned long long* d_counters = nullptr;  // 8 x u64
+    uint32_t* h_count = nullptr;               // pinned, polling ring
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return NRRT_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+static void free_scene(nrrt_ctx* ctx) {
+    for (auto t : ctx->tex_objs) cudaDestroyTextureObject(t);
+    for (auto a : ctx->tex_arrays) cudaFreeArray(a);
+    for (void* p : ctx->scene_allocs) cudaFree(p);
+    ctx->tex_objs.clear();
+    ctx->tex_arrays.clear();
+    ctx->scene_allocs.clear();
+    ctx->has_scene = false;
+}
+
+template <class T>
+static int upload(nrrt_ctx* ctx, const T* host, size_t count, const T** dev_out) {
+    *dev_out = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    ctx->scene_allocs.push_back(p);
+    if (count) {
+        if (!host) {
+            ctx->err = "scene array pointer is NULL";
+            return NRRT_ERR_INVALID;
+        }
+        CK(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    *dev_out = (const T*)p;
+    return NRRT_OK;
+}
+
+// noise 0.9.0 PermutationTable::new(seed): XorShiftRng seeded with [1, s, s, s] driving rand 0.8.5's
+// Fisher-Yates shuffle of 0..255 (SURVEY.md note A; recalled from the published sources, unpinned).
+static void noise_perm_table(uint32_t seed, uint8_t* out) {
+    uint32_t x = 1, y = seed, z = seed, w = seed;
+    for (int i = 0; i < 256; ++i) out[i] = (uint8_t)i;
+    for (uint32_t i = 255; i >= 1; --i) {
+        uint32_t range = i + 1, zone = (range << __builtin_clz(range)) - 1u, pick;
+        for (;;) {
+            uint32_t t = x ^ (x << 11);
+            x = y, y = z, z = w;
+            w = w ^ (w >> 19) ^ (t ^ (t >> 8));
+            uint64_t m = (uint64_t)w * range;
+            if ((uint32_t)m <= zone) {
+                pick = (uint32_t)(m >> 32);
+                break;
+            }
+        }
+        std::swap(out[i], out[pick]);
+    }
+}
+
+extern "C" {
+
+int nrrt_create(int device, nrrt_ctx** out) {
+    if (!out) return NRRT_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                         "); this library has no CPU fallback";
+        return NRRT_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        g_create_error = "device index out of range";
+        return NRRT_ERR_INVALID;
+    }
+    nrrt_ctx* ctx = new nrrt_ctx();
+    ctx->device = device;
+    auto bail = [&](const char* what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        delete ctx;
+        return NRRT_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaMalloc((void**)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess)
+        return bail("cudaMalloc", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_count, 64 * sizeof(uint32_t))) != cudaSuccess)
+        return bail("cudaMallocHost", e);
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    *out = ctx;
+    return NRRT_OK;
+}
+
+void nrrt_destroy(nrrt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->h_count) cudaFreeHost(ctx->h_count);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    delete ctx;
+}
+
+const char* nrrt_last_error(const nrrt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int nrrt_set_stream(nrrt_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return NRRT_ERR_INVALID;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return NRRT_OK;
+}
+
+int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
+    if (!ctx || !sc) return NRRT_ERR_INVALID;
+    if (sc->abi_version != NRRT_ABI_VERSION) {
+        ctx->err = "scene desc ABI version mismatch";
+        return NRRT_ERR_INVALID;
+    }
+    if (sc->max_stack > NRRT_STACK_CAP) {
+        ctx->err = "scene needs a deeper traversal stack than NRRT_STACK_CAP";
+        return NRRT_ERR_LIMIT;
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_scene(ctx);
+    DevScene D{};
+    int rc;
+#define UP(field, host, count)                                          \
+    if ((rc = upload(ctx, host, count, &D.field)) != NRRT_OK) {         \
+        free_scene(ctx);                                                \
+        return rc;                                                      \
+    }
+    const float4* nodes4 = nullptr;
+    if ((rc = upload(ctx, (const float4*)sc->nodes, (size_t)sc->n_nodes * 4, &nodes4)) != NRRT_OK) {
+        free_scene(ctx);
+        return rc;
+    }
+    D.nodes = nodes4;
+    UP(child_boxes, sc->child_boxes, (size_t)sc->n_nodes * 2);
+    D.root = sc->root;
+    D.root_box = sc->root_box;
+    UP(sphere_center, sc->sphere_center, (size_t)sc->n_spheres * 3);
+    UP(sphere_radius, sc->sphere_radius, sc->n_spheres);
+    UP(sphere_material, sc->sphere_material, sc->n_spheres);
+    UP(sphere_order, sc->sphere_order, sc->n_spheres);
+    UP(sphere_object, sc->sphere_object, sc->n_spheres);
+    UP(plane_p, sc->plane_p, (size_t)sc->n_planes * 3);
+    UP(plane_u, sc->plane_u, (size_t)sc->n_planes * 3);
+    UP(plane_v, sc->plane_v, (size_t)sc->n_planes * 3);
+    UP(plane_normal, sc->plane_normal, (size_t)sc->n_planes * 3);
+    UP(plane_w, sc->plane_w, (size_t)sc->n_planes * 3);
+    UP(plane_d, sc->plane_d, sc->n_planes);
+    UP(plane_material, sc->plane_material, sc->n_planes);
+    UP(plane_order, sc->plane_order, sc->n_planes);
+    UP(plane_object, sc->plane_object, sc->n_planes);
+    UP(instances, sc->instances, sc->n_instances);
+    UP(instance_order, sc->instance_order, sc->n_instances);
+    UP(xforms, sc->xforms, sc->n_xforms);
+    UP(materials, sc->materials, sc->n_materials);
+
+    // textures: fill noise defaults + the Fbm scale factor, build permutation tables
+    std::vector<nrrt_texture> tex(sc->textures, sc->textures + sc->n_textures);
+    std::vector<uint32_t> perm_base(std::max<uint32_t>(sc->n_textures, 1), 0);
+    std::vector<uint8_t> perm;
+    for (uint32_t i = 0; i < sc->n_textures; ++i) {
+        nrrt_texture& t = tex[i];
+        if (t.kind == NRRT_TEX_MARBLE) {  // Fbm::new(seed).set_octaves(7).set_frequency(f)  marble.rs:50-54
+            t.octaves = 7;
+            t.f1 = 3.14159265358979323846264338327950288 * 2.0 / 3.0;
+            t.f2 = 0.5;
+        }
+        if (t.kind == NRRT_TEX_NOISE || t.kind == NRRT_TEX_MARBLE) {
+            t.octaves = std::min<uint32_t>(std::max<uint32_t>(t.octaves, 1u), 32u);
+            double denom = 0.0;
+            for (uint32_t k = 1; k <= t.octaves; ++k) {  // 1 / sum persistence^k (powi by squaring)
+                double pw = 1.0, base = t.f2;
+                for (uint32_t e = k;;) {
+                    if (e & 1u) pw *= base;
+                    e >>= 1;
+                    if (!e) break;
+                    base *= base;
+                }
+                denom = denom + pw;
+            }
+            t.color[0] = 1.0 / denom;
+            perm_base[i] = (uint32_t)(perm.size() / 256);
+            for (uint32_t k = 0; k < t.octaves; ++k) {
+                perm.resize(perm.size() + 256);
+                noise_perm_table(t.seed + k, perm.data() + perm.size() - 256);
+            }
+        }
+    }
+    UP(textures, tex.data(), tex.size());
+    UP(perm, perm.data(), perm.size());
+    UP(perm_base, perm_base.data(), perm_base.size());
+
+    // per-material flag: does the texture chain read uv?  (checker.rs:82, image.rs:36-37)
+    std::vector<uint8_t> mflags(std::max<uint32_t>(sc->n_materials, 1), 0);
+    for (uint32_t i = 0; i < sc->n_materials; ++i) {
+        if (sc->materials[i].kind == NRRT_MAT_DIELECTRIC) continue;
+        uint32_t ti = sc->materials[i].texture;
+        if (ti < sc->n_textures && (tex[ti].kind == NRRT_TEX_CHECKER || tex[ti].kind == NRRT_TEX_IMAGE)) mflags[i] = 1;
+    }
+    UP(material_flags, mflags.data(), mflags.size());
+
+    // images -> CUDA texture objects (uchar4, point sampling, raw element reads)
+    std::vector<uint2> sizes(std::max<uint32_t>(sc->n_images, 1), make_uint2(1, 1));
+    std::vector<cudaTextureObject_t> objs(std::max<uint32_t>(sc->n_images, 1), 0);
+    for (uint32_t i = 0; i < sc->n_images; ++i) {
+        const nrrt_image& im = sc->images[i];
+        if (!im.rgb || !im.width || !im.height) {
+            ctx->err = "empty image";
+            free_scene(ctx);
+            return NRRT_ERR_INVALID;
+        }
+        std::vector<uchar4> rgba((size_t)im.width * im.height);
+        for (size_t k = 0; k < rgba.size(); ++k)
+            rgba[k] = make_uchar4(im.rgb[3 * k], im.rgb[3 * k + 1], im.rgb[3 * k + 2], 255);
+        cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr = nullptr;
+        CK(cudaMallocArray(&arr, &fmt, im.width, im.height));
+        ctx->tex_arrays.push_back(arr);
+        CK(cudaMemcpy2DToArray(arr, 0, 0, rgba.data(), (size_t)im.width * 4, (size_t)im.width * 4, im.height,
+                               cudaMemcpyHostToDevice));
+        cudaResourceDesc rd;
+        std::memset(&rd, 0, sizeof rd);
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        cudaTextureDesc td;
+        std::memset(&td, 0, sizeof td);
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t to = 0;
+        CK(cudaCreateTextureObject(&to, &rd, &td, nullptr));
+        ctx->tex_objs.push_back(to);
+        objs[i] = to;
+        sizes[i] = make_uint2(im.width, im.height);
+    }
+    UP(image_tex, objs.data(), objs.size());
+    UP(image_size, sizes.data(), sizes.size());
+#undef UP
+    D.n_nodes = sc->n_nodes, D.n_spheres = sc->n_spheres, D.n_planes = sc->n_planes;
+    D.n_instances = sc->n_instances, D.n_materials = sc->n_materials, D.n_textures = sc->n_textures;
+    CK(cudaStreamSynchronize(ctx->stream));  // host staging vectors die at return
+    ctx->dev = D;
+    ctx->max_stack = sc->max_stack;
+    ctx->has_scene = true;
+    return NRRT_OK;
+}
+
+static int ensure_scratch(nrrt_ctx* ctx, size_t bytes) {
+    if (ctx->scratch_bytes >= bytes) return NRRT_OK;
+    if (ctx->scratch) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(ctx->scratch));
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+    }
+    CK(cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return NRRT_OK;
+}
+
+int nrrt_trace_rays(nrrt_ctx* ctx, const double* rays, uint64_t n, double tmin, double tmax, uint32_t flags,
+                    nrrt_hit* out, nrrt_trace_stats* stats) {
+    if (!ctx) return NRRT_ERR_INVALID;
+    if (!ctx->has_scene) {
+        ctx->err = "nrrt_trace_rays before nrrt_scene_upload";
+        return NRRT_ERR_NO_SCENE;
+    }
+    if (n == 0) {
+        if (stats) std::memset(stats, 0, sizeof *stats);
+        return NRRT_OK;
+    }
+    if (!rays || !out) return NRRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const bool dev_buf = (flags & NRRT_TRACE_DEVICE_BUFFERS) != 0;
+    const double* d_rays = rays;
+    nrrt_hit* d_out = out;
+    if (!dev_buf) {
+        size_t rb = (size_t)n * 6 * sizeof(double), hb = (size_t)n * sizeof(nrrt_hit);
+        int rc = ensure_scratch(ctx, rb + hb);
+        if (rc != NRRT_OK) return rc;
+        d_rays = (const double*)ctx->scratch;
+        d_out = (nrrt_hit*)((char*)ctx->scratch + rb);
+        CK(cudaMemcpyAsync((void*)d_rays, rays, rb, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    dim3 grid((unsigned)((n + NRRT_BLOCK - 1) / NRRT_BLOCK)), block(NRRT_BLOCK);
+    size_t smem = (size_t)NRRT_BLOCK * NRRT_STACK_CAP * sizeof(uint32_t);
+    const bool count = stats != nullptr;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (flags & NRRT_TRACE_VISIT_ALL) {
+        if (count)
+            k_trace_rays<true, true><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, d_out, ctx->d_counters);
+        else
+            k_trace_rays<true, false><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, d_out, ctx->d_counters);
+    } else {
+        if (count)
+            k_trace_rays<false, true><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, d_out, ctx->d_counters);
+        else
+            k_trace_rays<false, false><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, d_out, ctx->d_counters);
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (!dev_buf) CK(cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(nrrt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long hc[3] = {0, 0, 0};
+    if (stats) CK(cudaMemcpyAsync(hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        stats->node_visits = hc[0];
+        stats->box_exact = hc[1];
+        stats->prim_tests = hc[2];
+        stats->kernel_ms = ms;
+    }
+    return NRRT_OK;
+}
+
+static uint32_t owned_rows(uint32_t H, uint32_t rank, uint32_t world, uint32_t R) {
+    uint32_t rows = 0;
+    for (uint32_t b = rank; (uint64_t)b * R < H; b += world) rows += std::min<uint32_t>(R, H - b * R);
+    return rows;
+}
+
+int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* opts_in, float* out_rgb,
+                nrrt_progress_fn progress, void* user, nrrt_render_stats* stats) {
+    if (!ctx) return NRRT_ERR_INVALID;
+    if (!ctx->has_scene) {
+        ctx->err = "nrrt_render before nrrt_scene_upload";
+        return NRRT_ERR_NO_SCENE;
+    }
+    if (!cam || !out_rgb || cam->width == 0 || cam->height == 0) {
+        ctx->err = "nrrt_render: bad camera or output pointer";
+        return NRRT_ERR_INVALID;
+    }
+    nrrt_render_opts o;
+    std::memset(&o, 0, sizeof o);
+    if (opts_in) o = *opts_in;
+    if (o.world == 0) o.world = 1;
+    if (o.rank >= o.world) {
+        ctx->err = "nrrt_render: rank >= world";
+        return NRRT_ERR_INVALID;
+    }
+    if (o.rows_per_block == 0) o.rows_per_block = 8;
+    CK(cudaSetDevice(ctx->device));
+
+    const uint32_t W = cam->width, H = cam->height;
+    const uint64_t total_pixels = (uint64_t)W * H;
+    if (total_pixels > 0x7FFFFFFFull) {
+        ctx->err = "image too large";
+        return NRRT_ERR_LIMIT;
+    }
+    nrrt_camera c = *cam;
+    if (c.samples_per_pixel < 1) c.samples_per_pixel = 1;  // camera.rs:104
+
+    RenderParams P;
+    P.key = make_uint2((uint32_t)o.seed, (uint32_t)(o.seed >> 32));
+    P.rank = o.rank, P.world = o.world, P.rows_per_block = o.rows_per_block;
+    P.n_owned_pixels = owned_rows(H, o.rank, o.world, o.rows_per_block) * W;
+    // sample lanes: keep >= ~1M paths in flight; depends on the full image only, so the per-pixel sum
+    // order (and the image, bit for bit) is the same for every GPU count
+    uint32_t lanes = 1;
+    const uint64_t target = o.max_slots ? o.max_slots : (1ull << 20);
+    while ((uint64_t)lanes * total_pixels < target && lanes * 2 <= c.samples_per_pixel) lanes *= 2;
+    P.lanes = lanes;
+    P.n_work = P.n_owned_pixels * lanes;
+
+    const bool out_dev = (o.flags & NRRT_RENDER_OUT_DEVICE) != 0;
+    const size_t fb_bytes = (size_t)total_pixels * 3 * sizeof(float);
+    const size_t n = P.n_work;
+    const bool wavefront = o.mode == NRRT_MODE_WAVEFRONT;
+    // scratch layout
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        size_t at = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return at;
+    };
+    size_t o_fb = out_dev ? 0 : carve(fb_bytes);
+    size_t o_acc = carve(n * 3 * sizeof(double));
+    size_t o_ray = 0, o_T = 0, o_L = 0, o_sample = 0, o_bounce = 0, o_ht = 0, o_hp = 0, o_hi = 0, o_q0 = 0, o_q1 = 0,
+           o_cnt = 0;
+    if (wavefront) {
+        o_ray = carve(n * 6 * sizeof(double));
+        o_T = carve(n * 3 * sizeof(double));
+        o_L = carve(n * 3 * sizeof(double));
+        o_sample = carve(n * sizeof(uint32_t));
+        o_bounce = carve(n * sizeof(uint32_t));
+        o_ht = carve(n * sizeof(double));
+        o_hp = carve(n * sizeof(uint32_t));
+        o_hi = carve(n * (1 + NRRT_MAX_INSTANCE_DEPTH) * sizeof(uint32_t));
+        o_q0 = carve(n * sizeof(uint32_t));
+        o_q1 = carve(n * sizeof(uint32_t));
+        o_cnt = carve(2 * sizeof(uint32_t));
+    }
+    int rc = ensure_scratch(ctx, std::max<size_t>(off, 256));
+    if (rc != NRRT_OK) return rc;
+    char* base = (char*)ctx->scratch;
+    float* d_fb = out_dev ? out_rgb : (float*)(base + o_fb);
+    double* d_acc = (double*)(base + o_acc);
+
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    uint64_t launches = 0, extend_launches = 0;
+    double extend_ms = 0.0;
+    const size_t smem = (size_t)NRRT_BLOCK * NRRT_STACK_CAP * sizeof(uint32_t);
+    const unsigned work_blocks = (unsigned)((n + NRRT_BLOCK - 1) / NRRT_BLOCK);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (n == 0 || c.ray_max_bounces == 0) {
+        // nothing owned, or every path returns black at depth 0 (camera.rs:276-278)
+        if (n) CK(cudaMemsetAsync(d_acc, 0, n * 3 * sizeof(double), ctx->stream));
+    } else if (!wavefront) {
+        k_render_mega<<<work_blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, c, P, d_acc, ctx->d_counters);
+        CK(cudaGetLastError());
+        ++launches;
+    } else {
+        WfState Wf;
+        Wf.ray = (double*)(base + o_ray);
+        Wf.T = (double*)(base + o_T);
+        Wf.L = (double*)(base + o_L);
+        Wf.acc = d_acc;
+        Wf.sample = (uint32_t*)(base + o_sample);
+        Wf.bounce = (uint32_t*)(base + o_bounce);
+        Wf.hit_t = (double*)(base + o_ht);
+        Wf.hit_prim = (uint32_t*)(base + o_hp);
+        Wf.hit_inst = (uint32_t*)(base + o_hi);
+        Wf.queue[0] = (uint32_t*)(base + o_q0);
+        Wf.queue[1] = (uint32_t*)(base + o_q1);
+        Wf.count = (uint32_t*)(base + o_cnt);
+        Wf.counters = ctx->d_counters;
+        k_wf_init<<<work_blocks, NRRT_BLOCK, 0, ctx->stream>>>(c, P, Wf);
+        CK(cudaGetLastError());
+        ++launches;
+        // the queue length lives on the device; the host polls it through a pinned ring without stalling
+        const int RING = 32, POLL_EVERY = 8;
+        while (ctx->ev_pool.size() < (size_t)RING + 2 * 64) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            ctx->ev_pool.push_back(e);
+        }
+        for (int k = 0; k < RING; ++k) ctx->h_count[k] = 0xFFFFFFFFu;
+        uint64_t iter = 0, polls_issued = 0, polls_seen = 0;
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
+        int timing_used = 0;
+        bool done = false;
+        uint32_t qin = 0;
+        const uint64_t hard_cap = ((uint64_t)(c.samples_per_pixel + lanes - 1) / lanes) * c.ray_max_bounces + 8;
+        while (!done && iter < hard_cap) {
+            bool timed = (iter % 16 == 0) && timing_used < 64;
+            cudaEvent_t ta = nullptr, tb = nullptr;
+            if (timed) {
+                ta = ctx->ev_pool[RING + 2 * timing_used], tb = ctx->ev_pool[RING + 2 * timing_used + 1];
+                CK(cudaEventRecord(ta, ctx->stream));
+            }
+            k_wf_extend<<<work_blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, Wf, (uint32_t)n, qin);
+            if (timed) {
+                CK(cudaEventRecord(tb, ctx->stream));
+                timing.emplace_back(ta, tb);
+                ++timing_used;
+            }
+            k_wf_shade<<<work_blocks, NRRT_BLOCK, 0, ctx->stream>>>(ctx->dev, c, P, Wf, qin);
+            CK(cudaGetLastError());
+            launches += 2;
+            ++extend_launches;
+            qin ^= 1;
+            ++iter;
+            if (iter % POLL_EVERY == 0) {
+                // throttle: never run more than RING polls ahead of the device
+                while (polls_issued - polls_seen >= (uint64_t)RING) {
+                    CK(cudaEventSynchronize(ctx->ev_pool[polls_seen % RING]));
+                    if (ctx->h_count[polls_seen % RING] == 0) done = true;
+                    ++polls_seen;
+                }
+                int slot = (int)(polls_issued % RING);
+                CK(cudaMemcpyAsync(&ctx->h_count[slot], Wf.count + qin, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+                CK(cudaEventRecord(ctx->ev_pool[slot], ctx->stream));
+                ++polls_issued;
+                while (polls_seen < polls_issued && cudaEventQuery(ctx->ev_pool[polls_seen % RING]) == cudaSuccess) {
+                    if (ctx->h_count[polls_seen % RING] == 0) done = true;
+                    ++polls_seen;
+                }
+                // once the queue is nearly drained, wait for each poll instead of launching empty passes
+                if (!done && polls_seen > 0 && ctx->h_count[(polls_seen - 1) % RING] < 4096u) {
+                    while (polls_seen < polls_issued) {
+                        CK(cudaEventSynchronize(ctx->ev_pool[polls_seen % RING]));
+                        if (ctx->h_count[polls_seen % RING] == 0) done = true;
+                        ++polls_seen;
+                    }
+                }
+            }
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        double sampled = 0.0;
+        for (auto& pr : timing) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+            sampled += ms;
+        }
+        if (!timing.empty()) extend_ms = sampled / (double)timing.size() * (double)extend_launches;
+    }
+    if (P.n_owned_pixels) {
+        k_resolve<<<(P.n_owned_pixels + 255) / 256, 256, 0, ctx->stream>>>(c, P, d_acc, d_fb);
+        CK(cudaGetLastError());
+        ++launches;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (!out_dev) {
+        // copy only the owned rows back into the caller's full-size buffer
+        const uint32_t R = o.rows_per_block;
+        for (uint32_t b = o.rank; (uint64_t)b * R < H; b += o.world) {
+            size_t y0 = (size_t)b * R, rows = std::min<size_t>(R, H - y0);
+            size_t offb = y0 * W * 3 * sizeof(float), bytes = rows * W * 3 * sizeof(float);
+            if (o.world == 1) {  // one contiguous copy
+                offb = 0, bytes = fb_bytes;
+            }
+            CK(cudaMemcpyAsync((char*)out_rgb + offb, (char*)d_fb + offb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            if (o.world == 1) break;
+        }
+    }
+    unsigned long long hc[2] = {0, 0};
+    CK(cudaMemcpyAsync(hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (progress) progress(P.n_owned_pixels, P.n_owned_pixels, user);
+    if (stats) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        stats->paths = wavefront ? hc[1] : hc[1];
+        stats->segments = hc[0];
+        stats->launches = launches;
+        stats->device_ms = ms;
+        stats->extend_ms = wavefront ? extend_ms : ms;
+        stats->extend_launches = wavefront ? extend_launches : (launches ? 1 : 0);
+        stats->pixels = P.n_owned_pixels;
+        stats->_pad = 0;
+    }
+    return NRRT_OK;
+}
+
+// struct sizes, so bindings can verify their mirror of the header
+size_t nrrt_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(nrrt_object);
+        case 1: return sizeof(nrrt_material);
+        case 2: return sizeof(nrrt_texture);
+        case 3: return sizeof(nrrt_image);
+        case 4: return sizeof(nrrt_graph_desc);
+        case 5: return sizeof(nrrt_camera_config);
+        case 6: return sizeof(nrrt_camera);
+        case 7: return sizeof(nrrt_node);
+        case 8: return sizeof(nrrt_box);
+        case 9: return sizeof(nrrt_xform);
+        case 10: return sizeof(nrrt_instance);
+        case 11: return sizeof(nrrt_scene_desc);
+        case 12: return sizeof(nrrt_hit);
+        case 13: return sizeof(nrrt_trace_stats);
+        case 14: return sizeof(nrrt_render_opts);
+        case 15: return sizeof(nrrt_render_stats);
+        default: return 0;
+    }
+}
+
+}  // extern "C"

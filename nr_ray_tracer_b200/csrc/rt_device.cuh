@@ -1,0 +1,703 @@
+// rt_device.cuh — device functions of the path-tracing hot path (sm_100a).
+//
+// Numerics contract (DESIGN.md "Exactness"):
+//  * everything that decides hit/miss, the winning primitive or t is f64 in the reference's
+//    operation order, written with __dadd_rn/__dmul_rn/__ddiv_rn/__dsqrt_rn so that nvcc can
+//    never contract a*b+c into an FMA (rustc does not) while f32 code keeps FMA;
+//  * f32 appears only in the box *filter*: a slab test on nearest-rounded f32 boxes with an
+//    explicit error margin that classifies a box as certain-hit / certain-miss / inconclusive;
+//    inconclusive inner nodes are re-tested with the reference's exact f64 slab test
+//    (aabb.rs:110-132), so the set of primitives that get tested is the reference's set
+//    restricted to those that can still win.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/nrrt.h"
+
+#define NRRT_STACK_CAP 32          // traversal stack entries per thread (host validates max_stack)
+#define NRRT_REF_POP 0xC0000000u   // type 6: "leave instance level" marker on the stack
+#define NRRT_INF __longlong_as_double(0x7ff0000000000000LL)
+
+// --------------------------------------------------------------------------- device scene
+struct DevScene {
+    const float4* nodes;  // 4 x float4 per node
+    const nrrt_box* child_boxes;
+    uint32_t root;
+    nrrt_box root_box;
+    const double* sphere_center;
+    const double* sphere_radius;
+    const uint32_t* sphere_material;
+    const uint32_t* sphere_order;
+    const uint32_t* sphere_object;
+    const double* plane_p;
+    const double* plane_u;
+    const double* plane_v;
+    const double* plane_normal;
+    const double* plane_w;
+    const double* plane_d;
+    const uint32_t* plane_material;
+    const uint32_t* plane_order;
+    const uint32_t* plane_object;
+    const nrrt_instance* instances;
+    const uint32_t* instance_order;
+    const nrrt_xform* xforms;
+    const nrrt_material* materials;
+    const nrrt_texture* textures;
+    const uint8_t* material_flags;  // bit0: texture chain needs uv
+    const cudaTextureObject_t* image_tex;
+    const uint2* image_size;
+    const uint8_t* perm;            // noise permutation tables, 256 B per (texture, octave)
+    const uint32_t* perm_base;      // per texture: first table index
+    uint32_t n_nodes, n_spheres, n_planes, n_instances, n_materials, n_textures;
+};
+
+// --------------------------------------------------------------------------- exact f64 helpers
+struct d3 {
+    double x, y, z;
+};
+__device__ __forceinline__ d3 mk3(double x, double y, double z) { return d3{x, y, z}; }
+__device__ __forceinline__ d3 ld3(const double* p) { return d3{p[0], p[1], p[2]}; }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ d3 add3(d3 a, d3 b) { return d3{xadd(a.x, b.x), xadd(a.y, b.y), xadd(a.z, b.z)}; }
+__device__ __forceinline__ d3 sub3(d3 a, d3 b) { return d3{xsub(a.x, b.x), xsub(a.y, b.y), xsub(a.z, b.z)}; }
+__device__ __forceinline__ d3 neg3(d3 a) { return d3{-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ d3 scale3(d3 a, double s) { return d3{xmul(a.x, s), xmul(a.y, s), xmul(a.z, s)}; }
+__device__ __forceinline__ d3 mul3(d3 a, d3 b) { return d3{xmul(a.x, b.x), xmul(a.y, b.y), xmul(a.z, b.z)}; }
+__device__ __forceinline__ d3 div3(d3 a, double s) { return d3{xdiv(a.x, s), xdiv(a.y, s), xdiv(a.z, s)}; }
+// glam dot: (x*x') + (y*y') + (z*z')
+__device__ __forceinline__ double dot3(d3 a, d3 b) {
+    return xadd(xadd(xmul(a.x, b.x), xmul(a.y, b.y)), xmul(a.z, b.z));
+}
+__device__ __forceinline__ d3 cross3(d3 a, d3 b) {
+    return d3{xsub(xmul(a.y, b.z), xmul(b.y, a.z)), xsub(xmul(a.z, b.x), xmul(b.z, a.x)),
+              xsub(xmul(a.x, b.y), xmul(b.x, a.y))};
+}
+// glam normalize: v * (1/sqrt(v.v))
+__device__ __forceinline__ d3 normalize3(d3 a) { return scale3(a, xdiv(1.0, __dsqrt_rn(dot3(a, a)))); }
+// ray.at(t) = origin + t*direction (ray.rs:40-42)
+__device__ __forceinline__ d3 ray_at(d3 o, d3 d, double t) { return add3(o, scale3(d, t)); }
+// Rust f64::signum
+__device__ __forceinline__ double signum(double x) {
+    if (x != x) return x;
+    return (__double_as_longlong(x) < 0) ? -1.0 : 1.0;
+}
+// DMat3 * v : c0*v.x + c1*v.y + c2*v.z, left to right (m = 9 doubles, column major)
+__device__ __forceinline__ d3 mat3_mul(const double* m, d3 v) {
+    d3 r = scale3(ld3(m), v.x);
+    r = add3(r, scale3(ld3(m + 3), v.y));
+    r = add3(r, scale3(ld3(m + 6), v.z));
+    return r;
+}
+// DMat4::transform_point3 / transform_vector3 on the xyz rows (m = 12 doubles: x,y,z,w columns)
+__device__ __forceinline__ d3 mat4_point(const double* m, d3 v) {
+    d3 r = scale3(ld3(m), v.x);
+    r = add3(scale3(ld3(m + 3), v.y), r);
+    r = add3(scale3(ld3(m + 6), v.z), r);
+    r = add3(ld3(m + 9), r);
+    return r;
+}
+__device__ __forceinline__ d3 mat4_vector(const double* m, d3 v) {
+    d3 r = scale3(ld3(m), v.x);
+    r = add3(scale3(ld3(m + 3), v.y), r);
+    r = add3(scale3(ld3(m + 6), v.z), r);
+    return r;
+}
+
+// --------------------------------------------------------------------------- wrappers
+// Ray into the object space of one instance (translate.rs:37-42, rotate.rs:91-97, scale.rs:73-78).
+__device__ __forceinline__ void xform_ray(const nrrt_xform* x, d3& o, d3& d) {
+    if (x->kind == NRRT_XF_TRANSLATE) {
+        o = sub3(o, ld3(x->to_obj));
+    } else if (x->kind == NRRT_XF_ROTATE) {
+        o = mat3_mul(x->to_obj, o);
+        d = mat3_mul(x->to_obj, d);
+    } else {
+        o = mat4_point(x->to_obj, o);
+        d = mat4_vector(x->to_obj, d);
+    }
+}
+__device__ __noinline__ void instance_ray(const DevScene& S, uint32_t inst, d3& o, d3& d) {
+    const nrrt_instance* in = &S.instances[inst];
+    uint32_t f = in->first_xform, n = in->n_xforms;
+    for (uint32_t k = 0; k < n; ++k) xform_ray(&S.xforms[f + k], o, d);
+}
+// Hit back to the parent space (translate.rs:45-48, rotate.rs:100-105, scale.rs:82-85: point only).
+__device__ __noinline__ void instance_hit_back(const DevScene& S, uint32_t inst, d3& point, d3& normal) {
+    const nrrt_instance* in = &S.instances[inst];
+    uint32_t f = in->first_xform, n = in->n_xforms;
+    for (uint32_t k = n; k-- > 0;) {
+        const nrrt_xform* x = &S.xforms[f + k];
+        if (x->kind == NRRT_XF_TRANSLATE) {
+            point = add3(point, ld3(x->to_obj));
+        } else if (x->kind == NRRT_XF_ROTATE) {
+            point = mat3_mul(x->to_world, point);
+            normal = mat3_mul(x->to_world, normal);
+        } else {
+            point = mat4_point(x->to_world, point);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------- exact box test
+// AABB::hit (aabb.rs:110-132) with Interval::ensure / intersection / is_empty (interval.rs:22-46).
+__device__ __noinline__ bool box_hit_exact(const nrrt_box* b, d3 o, d3 d, double tmin, double tmax) {
+    double lo = tmin, hi = tmax;
+    const double oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double t0 = xdiv(xsub(b->lo[a], oo[a]), dd[a]);
+        double t1 = xdiv(xsub(b->hi[a], oo[a]), dd[a]);
+        double mn, mx;
+        if (t0 < t1) {
+            mn = t0, mx = t1;
+        } else {
+            mn = t1, mx = t0;
+        }
+        lo = fmax(lo, mn);  // f64::max: NaN-ignoring, like CUDA fmax
+        hi = fmin(hi, mx);
+        if (lo > hi) return false;
+    }
+    return true;
+}
+
+// --------------------------------------------------------------------------- primitives
+// Sphere::hit (objects/sphere.rs:105-147): returns t or NaN for a miss.
+__device__ __forceinline__ double sphere_t(const DevScene& S, uint32_t i, d3 o, d3 d, double tmin, double tmax) {
+    d3 c = ld3(S.sphere_center + 3 * (size_t)i);
+    double r = S.sphere_radius[i];
+    d3 ec = sub3(c, o);
+    double a = dot3(d, d);
+    double h = dot3(ec, d);
+    double cc = xsub(dot3(ec, ec), xmul(r, r));
+    double disc = xsub(xmul(h, h), xmul(a, cc));
+    if (disc < 0.0) return __longlong_as_double(0x7ff8000000000000LL);
+    double sq = __dsqrt_rn(disc);
+    double t = xdiv(xsub(h, sq), a);
+    if (tmin < t && t < tmax) return t;  // Interval::surrounds
+    t = xdiv(xadd(h, sq), a);
+    if (tmin < t && t < tmax) return t;
+    return __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// Plane::hit (objects/plane.rs:141-174): returns t or NaN; alpha/beta through pointers.
+__device__ __forceinline__ double plane_t(const DevScene& S, uint32_t i, d3 o, d3 d, double tmin, double tmax,
+                                          double* alpha_out, double* beta_out) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    d3 n = ld3(S.plane_normal + 3 * (size_t)i);
+    double denom = dot3(n, d);
+    if (fabs(denom) < 1e-8) return nan;
+    double t = xdiv(xsub(S.plane_d[i], dot3(n, o)), denom);
+    if (!(tmin <= t && t <= tmax)) return nan;  // Interval::contains
+    d3 q = sub3(ray_at(o, d, t), ld3(S.plane_p + 3 * (size_t)i));
+    d3 w = ld3(S.plane_w + 3 * (size_t)i);
+    double alpha = dot3(w, cross3(q, ld3(S.plane_v + 3 * (size_t)i)));
+    double beta = dot3(w, cross3(ld3(S.plane_u + 3 * (size_t)i), q));
+    bool interior;
+    if (S.plane_material[i] & NRRT_PLANE_TRIANGLE_BIT)
+        interior = alpha > 0.0 && beta > 0.0 && xadd(alpha, beta) < 1.0;
+    else
+        interior = (0.0 <= alpha && alpha <= 1.0) && (0.0 <= beta && beta <= 1.0);
+    if (!interior) return nan;
+    *alpha_out = alpha;
+    *beta_out = beta;
+    return t;
+}
+
+// --------------------------------------------------------------------------- closest hit
+struct HitId {
+    double t;        // +inf = miss
+    uint32_t prim;   // NRRT_REF_NONE = miss
+    uint32_t depth;  // instance levels above prim
+    uint32_t inst[NRRT_MAX_INSTANCE_DEPTH];
+};
+
+struct TraceCounters {
+    uint32_t nodes, exact, prims;
+};
+
+__device__ __forceinline__ uint32_t leaf_order(const DevScene& S, uint32_t ref) {
+    uint32_t ty = NRRT_REF_TYPE(ref), ix = NRRT_REF_INDEX(ref);
+    if (ty == NRRT_REF_SPHERE) return S.sphere_order[ix];
+    if (ty == NRRT_REF_PLANE) return S.plane_order[ix];
+    return S.instance_order[ix];
+}
+
+// Equal-t tie: the reference keeps the right child (object.rs:110-114), i.e. the candidate that comes
+// later in depth-first leaf order wins.  Compare the two leaf paths level by level.
+__device__ __noinline__ bool tie_candidate_wins(const DevScene& S, uint32_t cand, const uint32_t* cur_inst,
+                                                uint32_t level, const HitId& best) {
+    for (uint32_t l = 0;; ++l) {
+        bool ca = l < level, cb = l < best.depth;
+        uint32_t ra = ca ? NRRT_REF(NRRT_REF_INSTANCE, cur_inst[l]) : cand;
+        uint32_t rb = cb ? NRRT_REF(NRRT_REF_INSTANCE, best.inst[l]) : best.prim;
+        if (ra != rb) return leaf_order(S, ra) > leaf_order(S, rb);
+        if (!ca || !cb) return false;  // same leaf
+    }
+}
+
+// Per-level f32 view of the ray for the box filter.
+struct Ray32 {
+    float idx, idy, idz;  // 1/d
+    float ox, oy, oz;     // o/d
+    float margin;         // absolute error term that depends on the ray only
+    bool degenerate;      // a zero/denormal direction component: filter disabled, exact test only
+};
+// relative error budget of one f32 slab distance: rounding of box, origin, 1/d, product (each 2^-24) + slack
+#define NRRT_BOX_EPS 4.0e-7f
+
+__device__ __forceinline__ Ray32 make_ray32(d3 o, d3 d) {
+    Ray32 r;
+    r.idx = __frcp_rn((float)d.x), r.idy = __frcp_rn((float)d.y), r.idz = __frcp_rn((float)d.z);
+    r.ox = (float)o.x * r.idx, r.oy = (float)o.y * r.idy, r.oz = (float)o.z * r.idz;
+    float om = fmaxf(fmaxf(fabsf(r.ox), fabsf(r.oy)), fabsf(r.oz));
+    r.margin = NRRT_BOX_EPS * 2.0f * om + 1e-30f;
+    float s = (r.idx + r.idy + r.idz) + (r.ox + r.oy + r.oz);  // inf or nan if any term is
+    r.degenerate = !(fabsf(s) < 3.0e38f) || !(om < 3.0e38f);
+    return r;
+}
+
+// f32 slab filter on one child box.  Returns gap = hi_min - lo_max (>= m: certain hit, < -m: certain
+// miss, otherwise inconclusive), the entry distance lo_max and the margin m.
+__device__ __forceinline__ void box_filter(const Ray32& r, float lx, float ly, float lz, float hx, float hy, float hz,
+                                           float tmin, float tmax, float& lo_max, float& gap, float& m) {
+    float ax = fmaf(lx, r.idx, -r.ox), bx = fmaf(hx, r.idx, -r.ox);
+    float ay = fmaf(ly, r.idy, -r.oy), by = fmaf(hy, r.idy, -r.oy);
+    float az = fmaf(lz, r.idz, -r.oz), bz = fmaf(hz, r.idz, -r.oz);
+    float lo = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+    float hi = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    lo_max = lo;
+    gap = hi - lo;
+    m = fmaf(NRRT_BOX_EPS, fmaxf(fabsf(lo), fabsf(hi)), r.margin);
+}
+
+// BVH::hit (objects/object.rs:89-121) over the flattened scene.
+//   VISIT_ALL = true : visits exactly the reference's node set (no pruning by the best hit so far)
+//   VISIT_ALL = false: near-first order + conservative pruning by the best t (same result, fewer visits)
+// `stack` is this thread's slice of shared memory, stride `sstride` (bank-conflict free).
+template <bool VISIT_ALL, bool COUNT>
+__device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, double tmin, double tmax,
+                                              volatile uint32_t* stack, uint32_t sstride, HitId& best,
+                                              TraceCounters* cnt) {
+    best.t = NRRT_INF;
+    best.prim = NRRT_REF_NONE;
+    best.depth = 0;
+#pragma unroll
+    for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) best.inst[k] = 0;
+
+    uint32_t cur_inst[NRRT_MAX_INSTANCE_DEPTH];
+#pragma unroll
+    for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) cur_inst[k] = 0;
+    uint32_t level = 0;
+    d3 o = wo, d = wd;
+    Ray32 r32 = make_ray32(o, d);
+    const float tmin32 = (float)tmin;                              // filter bounds; margins cover the rounding
+    const float tmax32 = (tmax < 3.0e38) ? (float)tmax : 3.4e38f;
+    float tcull = 3.4e38f;                                         // f32 upper bound of best.t (+ slack)
+
+    uint32_t sp = 0;
+    uint32_t cur = S.root;
+    // root of the scene: an inner node tests its own box (object.rs:102)
+    if (NRRT_REF_TYPE(cur) == NRRT_REF_NODE) {
+        if (COUNT) cnt->exact++;
+        if (!box_hit_exact(&S.root_box, o, d, tmin, tmax)) cur = NRRT_REF_NONE;
+    }
+
+    for (;;) {
+        uint32_t ty = NRRT_REF_TYPE(cur);
+        if (ty == NRRT_REF_NODE) {
+            // ---- inner node: filter both child boxes
+            uint32_t ni = NRRT_REF_INDEX(cur);
+            const float4* np = S.nodes + 4 * (size_t)ni;
+            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+            // layout: lo[0].xyz lo[1].xyz | hi[0].xyz hi[1].xyz | child[0] child[1] pad pad
+            uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+            if (COUNT) cnt->nodes++;
+            float e0, g0, m0, e1, g1, m1;
+            box_filter(r32, n0.x, n0.y, n0.z, n1.z, n1.w, n2.x, tmin32, tmax32, e0, g0, m0);
+            box_filter(r32, n0.w, n1.x, n1.y, n2.y, n2.z, n2.w, tmin32, tmax32, e1, g1, m1);
+            bool v0, v1;
+            {
+                bool leaf0 = NRRT_REF_TYPE(c0) != NRRT_REF_NODE, leaf1 = NRRT_REF_TYPE(c1) != NRRT_REF_NODE;
+                // leaves are not box-tested by the reference (object.rs:95-97): visit unless certainly missed
+                v0 = (c0 != NRRT_REF_NONE) && (r32.degenerate || !(g0 < -m0));
+                v1 = (c1 != NRRT_REF_NONE) && (r32.degenerate || !(g1 < -m1));
+                bool amb0 = v0 && !leaf0 && (r32.degenerate || !(g0 >= m0));
+                bool amb1 = v1 && !leaf1 && (r32.degenerate || !(g1 >= m1));
+                if (amb0) {
+                    if (COUNT) cnt->exact++;
+                    v0 = box_hit_exact(S.child_boxes + 2 * (size_t)ni, o, d, tmin, tmax);
+                }
+                if (amb1) {
+                    if (COUNT) cnt->exact++;
+                    v1 = box_hit_exact(S.child_boxes + 2 * (size_t)ni + 1, o, d, tmin, tmax);
+                }
+            }
+            if (!VISIT_ALL && !r32.degenerate) {
+                // prune children that start certainly behind the best hit (ties are kept: margin > 0)
+                v0 = v0 && !(e0 - m0 > tcull);
+                v1 = v1 && !(e1 - m1 > tcull);
+            }
+            if (v0 && v1) {
+                bool swap = !VISIT_ALL && (e1 < e0);
+                uint32_t nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
+                stack[sp * sstride] = farc;
+                ++sp;
+                cur = nearc;
+                continue;
+            }
+            if (v0) {
+                cur = c0;
+                continue;
+            }
+            if (v1) {
+                cur = c1;
+                continue;
+            }
+        } else if (ty == NRRT_REF_SPHERE || ty == NRRT_REF_PLANE) {
+            if (COUNT) cnt->prims++;
+            double a_, b_;
+            double t = (ty == NRRT_REF_SPHERE) ? sphere_t(S, NRRT_REF_INDEX(cur), o, d, tmin, tmax)
+                                               : plane_t(S, NRRT_REF_INDEX(cur), o, d, tmin, tmax, &a_, &b_);
+            if (t == t) {
+                bool take = t < best.t;
+                if (!take && t == best.t) take = tie_candidate_wins(S, cur, cur_inst, level, best);
+                if (take) {
+                    best.t = t;
+                    best.prim = cur;
+                    best.depth = level;
+#pragma unroll
+                    for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) best.inst[k] = cur_inst[k];
+                    // f32 upper bound of t with slack far above any f64 rounding discrepancy
+                    float tf = (float)t;
+                    tcull = tf + fabsf(tf) * 1.0e-6f + 1e-30f;
+                }
+            }
+        } else if (ty == NRRT_REF_INSTANCE) {
+            // ---- enter an instance: transform the ray, remember how to get back
+            uint32_t ii = NRRT_REF_INDEX(cur);
+            const nrrt_instance* in = &S.instances[ii];
+            uint32_t inner = in->inner;
+            if (inner != NRRT_REF_NONE && level < NRRT_MAX_INSTANCE_DEPTH) {
+                d3 no = o, nd = d;
+                instance_ray(S, ii, no, nd);
+                bool enter = true;
+                if (NRRT_REF_TYPE(inner) == NRRT_REF_NODE) {  // nested BVH root tests its own box
+                    if (COUNT) cnt->exact++;
+                    enter = box_hit_exact(&in->inner_box, no, nd, tmin, tmax);
+                }
+                if (enter) {
+                    stack[sp * sstride] = NRRT_REF_POP;
+                    ++sp;
+                    cur_inst[level] = ii;
+                    ++level;
+                    o = no, d = nd;
+                    r32 = make_ray32(o, d);
+                    cur = inner;
+                    continue;
+                }
+            }
+        } else if (cur == NRRT_REF_POP) {
+            // ---- leave the instance: rebuild the parent-level ray from the world ray
+            --level;
+            o = wo, d = wd;
+            for (uint32_t l = 0; l < level; ++l) instance_ray(S, cur_inst[l], o, d);
+            r32 = make_ray32(o, d);
+        }
+        // pop
+        if (sp == 0) break;
+        --sp;
+        cur = stack[sp * sstride];
+    }
+}
+
+// --------------------------------------------------------------------------- hit record
+struct HitRec {
+    d3 point, normal;
+    double u, v;
+    uint32_t material;
+    bool front_face;
+};
+
+// Rebuilds HitRecord (hitable.rs:38-59) of the winning primitive: object-space point/normal/uv from the
+// object-space ray, then back out through the wrappers.  want_uv=false skips the sphere's acos/atan2.
+__device__ __forceinline__ void resolve_hit(const DevScene& S, const HitId& h, d3 wo, d3 wd, bool want_uv,
+                                            HitRec& rec) {
+    d3 o = wo, d = wd;
+    for (uint32_t l = 0; l < h.depth; ++l) instance_ray(S, h.inst[l], o, d);
+    uint32_t ty = NRRT_REF_TYPE(h.prim), ix = NRRT_REF_INDEX(h.prim);
+    d3 point = ray_at(o, d, h.t), outward;
+    double u = 0.0, v = 0.0;
+    if (ty == NRRT_REF_SPHERE) {
+        d3 c = ld3(S.sphere_center + 3 * (size_t)ix);
+        outward = normalize3(sub3(point, c));  // sphere.rs:151
+        if (want_uv) {                         // sphere.rs:153-159
+            const double PI = 3.14159265358979323846264338327950288;
+            double theta = acos(-outward.y);
+            double phi = xadd(atan2(-outward.z, outward.x), PI);
+            u = xdiv(phi, xmul(2.0, PI));
+            v = xdiv(theta, PI);
+        }
+        rec.material = S.sphere_material[ix];
+    } else {
+        outward = ld3(S.plane_normal + 3 * (size_t)ix);
+        d3 q = sub3(point, ld3(S.plane_p + 3 * (size_t)ix));
+        d3 w = ld3(S.plane_w + 3 * (size_t)ix);
+        u = dot3(w, cross3(q, ld3(S.plane_v + 3 * (size_t)ix)));  // alpha
+        v = dot3(w, cross3(ld3(S.plane_u + 3 * (size_t)ix), q));  // beta
+        rec.material = S.plane_material[ix] & ~NRRT_PLANE_TRIANGLE_BIT;
+    }
+    double sign = signum(dot3(d, outward));
+    rec.front_face = sign < 0.0;
+    d3 normal = scale3(outward, -sign);
+    for (uint32_t l = h.depth; l-- > 0;) instance_hit_back(S, h.inst[l], point, normal);
+    rec.point = point;
+    rec.normal = normal;
+    rec.u = u;
+    rec.v = v;
+}
+
+// --------------------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 c) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ key.x, lo1, hi0 ^ c.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return c;
+}
+// counter = (pixel, sample, stage<<12 | iter, 0): stage 0 = camera, stage k+1 = scatter at bounce k
+struct Sampler {
+    uint2 key;
+    uint32_t pixel, sample;
+    __device__ __forceinline__ uint4 draw(uint32_t stage, uint32_t iter) const {
+        return philox4x32_10(key, make_uint4(pixel, sample, (stage << 12) | (iter & 0xFFFu), 0u));
+    }
+};
+__device__ __forceinline__ double u_m1_1(uint32_t r) { return xsub(xmul((double)r, 1.0 / 2147483648.0), 1.0); }
+__device__ __forceinline__ double u_mh_h(uint32_t r) { return xsub(xmul((double)r, 1.0 / 4294967296.0), 0.5); }
+__device__ __forceinline__ double u_0_1(uint32_t r) { return xmul((double)r, 1.0 / 4294967296.0); }
+
+// vector.rs:61-70 — p/|p|^2, |p|^2 in (1e-160, 1]
+__device__ __forceinline__ d3 random_in_unit_sphere(const Sampler& s, uint32_t stage) {
+    for (uint32_t it = 0;; ++it) {
+        uint4 r = s.draw(stage, it);
+        d3 p = mk3(u_m1_1(r.x), u_m1_1(r.y), u_m1_1(r.z));
+        double l2 = dot3(p, p);
+        if ((1e-160 < l2 && l2 <= 1.0) || it == 0xFFFu) return div3(p, l2);
+    }
+}
+// vector.rs:72-81 — p/|p|^2, |p|^2 < 1
+__device__ __forceinline__ d3 random_in_unit_disk(const Sampler& s) {
+    for (uint32_t it = 1;; ++it) {
+        uint4 r = s.draw(0, it);
+        d3 p = mk3(u_m1_1(r.x), u_m1_1(r.y), 0.0);
+        double l2 = dot3(p, p);
+        if (l2 < 1.0 || it == 0xFFFu) return div3(p, l2);
+    }
+}
+
+// --------------------------------------------------------------------------- textures
+// noise 0.9.0 Perlin (restated from the published algorithm; see oracle.cpp / DESIGN.md).
+__device__ __forceinline__ double grad3(uint32_t h, double x, double y, double z) {
+    switch (h & 15u) {
+        case 0: case 12: return xadd(x, y);
+        case 1: case 13: return xadd(-x, y);
+        case 2: return xsub(x, y);
+        case 3: return xsub(-x, y);
+        case 4: return xadd(x, z);
+        case 5: return xadd(-x, z);
+        case 6: return xsub(x, z);
+        case 7: return xsub(-x, z);
+        case 8: return xadd(y, z);
+        case 9: case 14: return xadd(-y, z);
+        case 10: return xsub(y, z);
+        default: return xsub(-y, z);
+    }
+}
+__device__ __forceinline__ double quintic(double t) {
+    return xmul(xmul(xmul(t, t), t), xadd(xmul(t, xsub(xmul(t, 6.0), 15.0)), 10.0));
+}
+__device__ __noinline__ double perlin3(const uint8_t* __restrict__ pm, double px, double py, double pz) {
+    double fx = floor(px), fy = floor(py), fz = floor(pz);
+    long long cx = (long long)fx, cy = (long long)fy, cz = (long long)fz;
+    double dx = xsub(px, fx), dy = xsub(py, fy), dz = xsub(pz, fz);
+    double g[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int ox = k & 1, oy = (k >> 1) & 1, oz = (k >> 2) & 1;
+        uint32_t i = (uint32_t)((cx + ox) & 0xff);
+        i = (uint32_t)__ldg(pm + i) ^ (uint32_t)((cy + oy) & 0xff);
+        i = (uint32_t)__ldg(pm + i) ^ (uint32_t)((cz + oz) & 0xff);
+        uint32_t h = __ldg(pm + i);
+        g[k] = grad3(h, xsub(dx, (double)ox), xsub(dy, (double)oy), xsub(dz, (double)oz));
+    }
+    // g index: bit0 = x, bit1 = y, bit2 = z
+    double g000 = g[0], g100 = g[1], g010 = g[2], g110 = g[3], g001 = g[4], g101 = g[5], g011 = g[6], g111 = g[7];
+    double u = quintic(dx), v = quintic(dy), w = quintic(dz);
+    double k0 = g000;
+    double k1 = xsub(g100, g000);
+    double k2 = xsub(g010, g000);
+    double k3 = xsub(g001, g000);
+    double k4 = xsub(xsub(xadd(g000, g110), g100), g010);
+    double k5 = xsub(xsub(xadd(g000, g101), g100), g001);
+    double k6 = xsub(xsub(xadd(g000, g011), g010), g001);
+    double k7 = xsub(xsub(xsub(xsub(xadd(xadd(xadd(g100, g010), g001), g111), g000), g110), g101), g011);
+    double r = k0;
+    r = xadd(r, xmul(k1, u));
+    r = xadd(r, xmul(k2, v));
+    r = xadd(r, xmul(k3, w));
+    r = xadd(r, xmul(xmul(k4, u), v));
+    r = xadd(r, xmul(xmul(k5, u), w));
+    r = xadd(r, xmul(xmul(k6, v), w));
+    r = xadd(r, xmul(xmul(xmul(k7, u), v), w));
+    r = xmul(r, 1.1547005383792515);
+    return r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+}
+// Fbm<Perlin>::get
+__device__ __noinline__ double fbm3(const DevScene& S, uint32_t tex, uint32_t octaves, double freq, double lac,
+                                    double pers, double scale_factor, d3 p) {
+    const uint8_t* tables = S.perm + 256 * (size_t)S.perm_base[tex];
+    double x = xmul(p.x, freq), y = xmul(p.y, freq), z = xmul(p.z, freq);
+    double result = 0.0, att = pers;
+    for (uint32_t i = 0; i < octaves; ++i) {
+        double s = perlin3(tables + 256 * (size_t)i, x, y, z);
+        s = xmul(s, att);
+        att = xmul(att, pers);
+        result = xadd(result, s);
+        x = xmul(x, lac), y = xmul(y, lac), z = xmul(z, lac);
+    }
+    return xmul(result, scale_factor);
+}
+
+__device__ __forceinline__ unsigned long long sat_u64(double x) {  // Rust `as u64`
+    if (!(x == x) || x <= 0.0) return 0ull;
+    if (x >= 18446744073709551615.0) return 0xFFFFFFFFFFFFFFFFull;
+    return (unsigned long long)x;
+}
+__device__ __forceinline__ uint32_t sat_u32(double x) {  // Rust `as u32`
+    if (!(x == x) || x <= 0.0) return 0u;
+    if (x >= 4294967295.0) return 0xFFFFFFFFu;
+    return (uint32_t)x;
+}
+
+// Texture::get_color (textures/*.rs).  Checker recursion is a loop: sub-textures always precede.
+__device__ __forceinline__ d3 texture_color(const DevScene& S, uint32_t tex, double u, double v, d3 point) {
+    for (int guard = 0; guard < 64; ++guard) {
+        const nrrt_texture* t = &S.textures[tex];
+        uint32_t kind = t->kind;
+        if (kind == NRRT_TEX_SOLID) return ld3(t->color);
+        if (kind == NRRT_TEX_CHECKER) {  // checker.rs:77-89
+            unsigned long long s = sat_u64(xmul(u, t->f0)) + sat_u64(xmul(v, t->f0));
+            tex = (s % 2ull == 0ull) ? t->a : t->b;
+            continue;
+        }
+        if (kind == NRRT_TEX_IMAGE) {  // image.rs:30-40 — nearest texel, u8/255 as f32, no sRGB decode
+            uint2 sz = S.image_size[t->a];
+            double cu = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+            double cv = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+            uint32_t x = sat_u32(xmul(cu, (double)sz.x));
+            uint32_t y = sat_u32(xmul(xsub(1.0, cv), (double)sz.y));
+            if (x >= sz.x) x = sz.x - 1;  // the reference panics here (u == 1 / v == 0)
+            if (y >= sz.y) y = sz.y - 1;
+            uchar4 px = tex2D<uchar4>(S.image_tex[t->a], (float)x + 0.5f, (float)y + 0.5f);
+            return mk3((double)__fdiv_rn((float)px.x, 255.0f), (double)__fdiv_rn((float)px.y, 255.0f),
+                       (double)__fdiv_rn((float)px.z, 255.0f));
+        }
+        // NOISE (noise.rs:135-145) / MARBLE (marble.rs:86-97); f1/f2 hold lacunarity/persistence,
+        // color[0] holds the precomputed Fbm scale factor (filled at upload)
+        double n = fabs(fbm3(S, tex, t->octaves, t->f0, t->f1, t->f2, t->color[0], point));
+        if (kind == NRRT_TEX_NOISE) return mk3(n, n, n);
+        double val = xdiv(xadd(1.0, sin(xadd(xmul(t->f0, point.z), xmul(10.0, n)))), 2.0);
+        return mk3(val, val, val);
+    }
+    return mk3(0.0, 0.0, 0.0);
+}
+
+// --------------------------------------------------------------------------- materials
+// Returns true if the path continues.  emitted is always set (material.rs:20-26, diffuse_light.rs:63-75).
+__device__ __forceinline__ bool shade_hit(const DevScene& S, const HitRec& h, d3 rd, bool primary, const Sampler& smp,
+                                          uint32_t stage, d3& emitted, d3& atten, d3& new_dir) {
+    const nrrt_material* m = &S.materials[h.material];
+    uint32_t kind = m->kind;
+    emitted = mk3(0.0, 0.0, 0.0);
+    if (kind == NRRT_MAT_LAMBERTIAN) {  // lambertian.rs:39-55
+        d3 dir = add3(h.normal, random_in_unit_sphere(smp, stage));
+        if (fabs(dir.x) < 1e-8 && fabs(dir.y) < 1e-8 && fabs(dir.z) < 1e-8) dir = h.normal;
+        new_dir = dir;
+        atten = texture_color(S, m->texture, h.u, h.v, h.point);
+        return true;
+    }
+    if (kind == NRRT_MAT_METAL) {  // metal.rs:73-91
+        d3 refl = sub3(rd, scale3(h.normal, xmul(2.0, dot3(rd, h.normal))));  // glam reflect
+        d3 dir = add3(normalize3(refl), scale3(random_in_unit_sphere(smp, stage), m->param));
+        if (dot3(dir, h.normal) > 0.0) {
+            new_dir = dir;
+            atten = texture_color(S, m->texture, h.u, h.v, h.point);
+            return true;
+        }
+        return false;
+    }
+    if (kind == NRRT_MAT_DIELECTRIC) {  // dielectric.rs:39-67
+        double ri = h.front_face ? xdiv(1.0, m->param) : m->param;
+        d3 unit = normalize3(rd);
+        double cos_theta = fmin(dot3(neg3(unit), h.normal), 1.0);
+        double sin_theta = __dsqrt_rn(xsub(1.0, xmul(cos_theta, cos_theta)));
+        bool refl = xmul(ri, sin_theta) > 1.0;
+        if (!refl) {
+            double r0 = xdiv(xsub(1.0, ri), xadd(1.0, ri));  // reflectance :13-19
+            r0 = xmul(r0, r0);
+            double x = xsub(1.0, cos_theta);
+            double x2 = xmul(x, x);
+            double x5 = xmul(x, xmul(x2, x2));
+            double p = xadd(r0, xmul(xsub(1.0, r0), x5));
+            refl = p > u_0_1(smp.draw(stage, 0).x);
+        }
+        if (refl) {
+            new_dir = sub3(unit, scale3(h.normal, xmul(2.0, dot3(unit, h.normal))));
+        } else {  // glam refract
+            double ndi = dot3(h.normal, unit);
+            double k = xsub(1.0, xmul(xmul(ri, ri), xsub(1.0, xmul(ndi, ndi))));
+            if (k >= 0.0)
+                new_dir = sub3(scale3(unit, ri), scale3(h.normal, xadd(xmul(ri, ndi), __dsqrt_rn(k))));
+            else
+                new_dir = mk3(0.0, 0.0, 0.0);
+        }
+        atten = mk3(1.0, 1.0, 1.0);
+        return true;
+    }
+    // DiffuseLight: emits, never scatters.  Seen by a camera ray it shows at x1 (quirk Q3).
+    double k = primary ? 1.0 : m->param;
+    emitted = scale3(texture_color(S, m->texture, h.u, h.v, h.point), k);
+    return false;
+}
+
+// --------------------------------------------------------------------------- camera
+// Camera::get_ray (camera.rs:244-267)
+__device__ __forceinline__ void camera_ray(const nrrt_camera& cam, uint32_t x, uint32_t y, const Sampler& s, d3& o,
+                                           d3& d) {
+    double ox = 0.0, oy = 0.0;
+    if (cam.samples_per_pixel > 1) {
+        uint4 r = s.draw(0, 0);
+        ox = u_mh_h(r.x);
+        oy = u_mh_h(r.y);
+    }
+    d3 point = add3(add3(ld3(cam.viewport_top_left), scale3(ld3(cam.pixel_delta_u), xadd((double)x, ox))),
+                    scale3(ld3(cam.pixel_delta_v), xadd((double)y, oy)));
+    d3 ddu = ld3(cam.defocus_disk_u), ddv = ld3(cam.defocus_disk_v);
+    bool no_lens = ddu.x == 0.0 && ddu.y == 0.0 && ddu.z == 0.0 && ddv.x == 0.0 && ddv.y == 0.0 && ddv.z == 0.0;
+    if (no_lens) {
+        o = add3(add3(ld3(cam.look_from), mk3(0.0, 0.0, 0.0)), mk3(0.0, 0.0, 0.0));
+    } else {
+        d3 p = random_in_unit_disk(s);
+        o = add3(add3(ld3(cam.look_from), scale3(ddu, p.x)), scale3(ddv, p.y));
+    }
+    d = sub3(point, o);
+}

@@ -20,8 +20,8 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "oracle.cpp")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "oracle.cpp"), os.path.join(_HERE, "..", "include", "nrrt.h")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "liboracle.so"], check=True, capture_output=True)
     return _LIB_PATH
 
@@ -29,8 +29,7 @@ def build(force: bool = False) -> str:
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
-            build()
+        build()
         L = C.CDLL(_LIB_PATH)
         L.oracle_build.restype = C.c_void_p
         L.oracle_build.argtypes = [C.POINTER(A.GraphDesc)]

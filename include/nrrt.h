@@ -333,7 +333,8 @@ typedef struct nrrt_render_opts {
 
 enum {
     NRRT_RENDER_OUT_HOST = 0,
-    NRRT_RENDER_OUT_DEVICE = 1 /* out_rgb is a device pointer */
+    NRRT_RENDER_OUT_DEVICE = 1, /* out_rgb is a device pointer */
+    NRRT_RENDER_COUNT = 2       /* instrumented megakernel: also count node visits / primitive tests (slower) */
 };
 
 typedef struct nrrt_render_stats {
@@ -345,6 +346,9 @@ typedef struct nrrt_render_stats {
     uint64_t extend_launches;
     uint32_t pixels;       /* pixels owned by this rank                        */
     uint32_t _pad;
+    uint64_t node_visits;  /* NRRT_RENDER_COUNT only: inner nodes fetched      */
+    uint64_t box_exact;    /*   f32-inconclusive / root box tests done in f64  */
+    uint64_t prim_tests;   /*   exact primitive tests                          */
 } nrrt_render_stats;
 
 typedef void (*nrrt_progress_fn)(uint64_t pixels_done, uint64_t pixels_total, void* user);

@@ -24,7 +24,7 @@ REF_INDEX_MASK = 0x1FFFFFFF
 
 TRACE_ORDERED, TRACE_VISIT_ALL, TRACE_DEVICE_BUFFERS = 0, 1, 2
 MODE_WAVEFRONT, MODE_MEGAKERNEL = 0, 1
-RENDER_OUT_HOST, RENDER_OUT_DEVICE = 0, 1
+RENDER_OUT_HOST, RENDER_OUT_DEVICE, RENDER_COUNT = 0, 1, 2
 MAX_INSTANCE_DEPTH = 4
 
 u32, u64, f64, f32 = C.c_uint32, C.c_uint64, C.c_double, C.c_float
@@ -121,7 +121,8 @@ class RenderOpts(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("paths", u64), ("segments", u64), ("launches", u64), ("device_ms", f64), ("extend_ms", f64),
-                ("extend_launches", u64), ("pixels", u32), ("_pad", u32)]
+                ("extend_launches", u64), ("pixels", u32), ("_pad", u32),
+                ("node_visits", u64), ("box_exact", u64), ("prim_tests", u64)]
 
 
 PROGRESS_FN = C.CFUNCTYPE(None, u64, u64, C.c_void_p)

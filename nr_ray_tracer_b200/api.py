@@ -163,12 +163,14 @@ class Context:
         return {"node_visits": st.node_visits, "box_exact": st.box_exact, "prim_tests": st.prim_tests,
                 "kernel_ms": st.kernel_ms}
 
-    def render(self, cam: A.Camera, out: Optional[np.ndarray] = None, seed: int = 0, mode: int = A.MODE_MEGAKERNEL,
+    def render(self, cam: A.Camera, out: Optional[np.ndarray] = None, seed: int = 0, mode: int = A.MODE_WAVEFRONT,
                rank: int = 0, world: int = 1, rows_per_block: int = 0, max_slots: int = 0,
-               out_device_ptr: Optional[int] = None, progress: Optional[Callable[[int, int], None]] = None):
+               out_device_ptr: Optional[int] = None, progress: Optional[Callable[[int, int], None]] = None,
+               count: bool = False):
         """Camera::render.  Returns (image (H, W, 3) float32 or None for device output, stats dict)."""
         opts = A.RenderOpts(seed=seed, mode=mode, rank=rank, world=world, rows_per_block=rows_per_block,
-                            max_slots=max_slots, flags=A.RENDER_OUT_DEVICE if out_device_ptr is not None else 0)
+                            max_slots=max_slots, flags=(A.RENDER_OUT_DEVICE if out_device_ptr is not None else 0) |
+                            (A.RENDER_COUNT if count else 0))
         st = A.RenderStats()
         cb = A.PROGRESS_FN(lambda done, total, user: progress(done, total)) if progress else None
         if out_device_ptr is not None:
@@ -181,7 +183,8 @@ class Context:
         self._check(lib().nrrt_render(self._h, C.byref(cam), C.byref(opts), ptr, C.cast(cb, C.c_void_p) if cb else None,
                                       None, C.byref(st)))
         stats = {k: getattr(st, k) for k in ("paths", "segments", "launches", "device_ms", "extend_ms",
-                                             "extend_launches", "pixels")}
+                                             "extend_launches", "pixels", "node_visits", "box_exact",
+                                             "prim_tests")}
         return (None if out_device_ptr is not None else out), stats
 
 

@@ -109,12 +109,14 @@ __device__ __forceinline__ bool path_step(const DevScene& S, const nrrt_camera& 
     return bounce < cam.ray_max_bounces;  // camera.rs:276-278
 }
 
+template <bool COUNT>
 __global__ void __launch_bounds__(NRRT_BLOCK)
 k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_camera cam,
               const __grid_constant__ RenderParams P, double* __restrict__ acc, unsigned long long* __restrict__ counters) {
     extern __shared__ uint32_t s_stack[];
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long segs = 0, paths = 0;
+    TraceCounters tc{0, 0, 0};
     if (w < P.n_work) {
         uint32_t lane = w / P.n_owned_pixels, po = w - lane * P.n_owned_pixels;
         uint32_t x, y;
@@ -136,7 +138,7 @@ k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
                 ++paths;
             }
             HitId h;
-            trace_closest<false, false>(S, o, d, 0.001, NRRT_INF, s_stack + threadIdx.x, blockDim.x, h, nullptr);
+            trace_closest<false, COUNT>(S, o, d, 0.001, NRRT_INF, s_stack + threadIdx.x, blockDim.x, h, &tc);
             ++segs;
             alive = path_step(S, cam, h, smp, o, d, T, L, bounce);
             if (!alive) {
@@ -163,6 +165,11 @@ k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
     if (threadIdx.x == 0) {
         atomicAdd(&counters[0], s_cnt[0]);
         atomicAdd(&counters[1], s_cnt[1]);
+    }
+    if (COUNT) {
+        atomicAdd(&counters[2], (unsigned long long)tc.nodes);
+        atomicAdd(&counters[3], (unsigned long long)tc.exact);
+        atomicAdd(&counters[4], (unsigned long long)tc.prims);
     }
 }
 
@@ -711,7 +718,8 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     const bool out_dev = (o.flags & NRRT_RENDER_OUT_DEVICE) != 0;
     const size_t fb_bytes = (size_t)total_pixels * 3 * sizeof(float);
     const size_t n = P.n_work;
-    const bool wavefront = o.mode == NRRT_MODE_WAVEFRONT;
+    const bool counting = (o.flags & NRRT_RENDER_COUNT) != 0;
+    const bool wavefront = o.mode == NRRT_MODE_WAVEFRONT && !counting;
     // scratch layout
     size_t off = 0;
     auto carve = [&](size_t bytes) {
@@ -752,7 +760,10 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         // nothing owned, or every path returns black at depth 0 (camera.rs:276-278)
         if (n) CK(cudaMemsetAsync(d_acc, 0, n * 3 * sizeof(double), ctx->stream));
     } else if (!wavefront) {
-        k_render_mega<<<work_blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, c, P, d_acc, ctx->d_counters);
+        if (counting)
+            k_render_mega<true><<<work_blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, c, P, d_acc, ctx->d_counters);
+        else
+            k_render_mega<false><<<work_blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, c, P, d_acc, ctx->d_counters);
         CK(cudaGetLastError());
         ++launches;
     } else {
@@ -860,14 +871,14 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
             if (o.world == 1) break;
         }
     }
-    unsigned long long hc[2] = {0, 0};
+    unsigned long long hc[5] = {0, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (progress) progress(P.n_owned_pixels, P.n_owned_pixels, user);
     if (stats) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        stats->paths = wavefront ? hc[1] : hc[1];
+        stats->paths = hc[1];
         stats->segments = hc[0];
         stats->launches = launches;
         stats->device_ms = ms;
@@ -875,6 +886,9 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         stats->extend_launches = wavefront ? extend_launches : (launches ? 1 : 0);
         stats->pixels = P.n_owned_pixels;
         stats->_pad = 0;
+        stats->node_visits = hc[2];
+        stats->box_exact = hc[3];
+        stats->prim_tests = hc[4];
     }
     return NRRT_OK;
 }

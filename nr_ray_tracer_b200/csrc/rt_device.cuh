@@ -505,7 +505,7 @@ __device__ __forceinline__ d3 random_in_unit_disk(const Sampler& s) {
 }
 
 // --------------------------------------------------------------------------- textures
-// noise 0.9.0 Perlin (restated from the published algorithm; see oracle.cpp / DESIGN.md).
+// noise 0.9.0 Perlin (restated from the published algorithm).
 __device__ __forceinline__ double grad3(uint32_t h, double x, double y, double z) {
     switch (h & 15u) {
         case 0: case 12: return xadd(x, y);

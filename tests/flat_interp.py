@@ -1,0 +1,193 @@
+"""Pure-Python interpreter of the flat device layout (include/nrrt.h) with the REFERENCE's traversal
+semantics (visit both children, exact f64 slab test, one primitive per leaf, ties to the later leaf).
+
+Test infrastructure: it lets the CPU-only suite check the product's host flattening (csrc/host_scene.cpp)
+against the oracle without a GPU.  Python floats are IEEE doubles and never fuse multiply-add, so the
+arithmetic below is bit-faithful to the reference's operation order.  Slow: use a few thousand rays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from nr_ray_tracer_b200 import _abi as A
+
+INF = float("inf")
+
+
+def _arr(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    ct = {np.float64: C.c_double, np.uint32: C.c_uint32}[dtype]
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).copy()
+
+
+class FlatScene:
+    def __init__(self, host_scene):
+        d = host_scene.desc
+        self.d = d
+        self.nodes = host_scene.nodes()
+        self.child_boxes = host_scene.child_boxes()  # (n, 2 children, lo/hi, 3)
+        self.root = d.root
+        self.root_box = (list(d.root_box.lo), list(d.root_box.hi))
+        ns, npl = d.n_spheres, d.n_planes
+        self.sc = _arr(d.sphere_center, ns * 3, np.float64).reshape(-1, 3)
+        self.sr = _arr(d.sphere_radius, ns, np.float64)
+        self.sm = _arr(d.sphere_material, ns, np.uint32)
+        self.so = _arr(d.sphere_order, ns, np.uint32)
+        self.sobj = _arr(d.sphere_object, ns, np.uint32)
+        self.pp = _arr(d.plane_p, npl * 3, np.float64).reshape(-1, 3)
+        self.pu = _arr(d.plane_u, npl * 3, np.float64).reshape(-1, 3)
+        self.pv = _arr(d.plane_v, npl * 3, np.float64).reshape(-1, 3)
+        self.pn = _arr(d.plane_normal, npl * 3, np.float64).reshape(-1, 3)
+        self.pw = _arr(d.plane_w, npl * 3, np.float64).reshape(-1, 3)
+        self.pd = _arr(d.plane_d, npl, np.float64)
+        self.pm = _arr(d.plane_material, npl, np.uint32)
+        self.po = _arr(d.plane_order, npl, np.uint32)
+        self.pobj = _arr(d.plane_object, npl, np.uint32)
+        self.inst = [d.instances[i] for i in range(d.n_instances)]
+        self.inst_order = _arr(d.instance_order, d.n_instances, np.uint32)
+        self.xf = [d.xforms[i] for i in range(d.n_xforms)]
+
+
+def _dot(a, b):
+    return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]
+
+
+def _cross(a, b):
+    return (a[1] * b[2] - b[1] * a[2], a[2] * b[0] - b[2] * a[0], a[0] * b[1] - b[0] * a[1])
+
+
+def _div(a, b):
+    try:
+        return a / b
+    except ZeroDivisionError:
+        if a != a or a == 0.0:
+            return float("nan")
+        neg = (math.copysign(1.0, a) < 0) != (math.copysign(1.0, b) < 0)
+        return -INF if neg else INF
+
+
+def _fmax(a, b):
+    if a != a:
+        return b
+    if b != b:
+        return a
+    return a if a > b else b
+
+
+def _fmin(a, b):
+    if a != a:
+        return b
+    if b != b:
+        return a
+    return a if a < b else b
+
+
+def box_hit(lo, hi, o, d, tmin, tmax):
+    a, b = tmin, tmax
+    for k in range(3):
+        t0, t1 = _div(lo[k] - o[k], d[k]), _div(hi[k] - o[k], d[k])
+        mn, mx = (t0, t1) if t0 < t1 else (t1, t0)
+        a, b = _fmax(a, mn), _fmin(b, mx)
+        if a > b:
+            return False
+    return True
+
+
+def _mat3(m, v):
+    r = [m[0 + i] * v[0] for i in range(3)]
+    r = [r[i] + m[3 + i] * v[1] for i in range(3)]
+    return [r[i] + m[6 + i] * v[2] for i in range(3)]
+
+
+def _mat4(m, v, point):
+    r = [m[0 + i] * v[0] for i in range(3)]
+    r = [m[3 + i] * v[1] + r[i] for i in range(3)]
+    r = [m[6 + i] * v[2] + r[i] for i in range(3)]
+    if point:
+        r = [m[9 + i] + r[i] for i in range(3)]
+    return r
+
+
+def trace(fs: FlatScene, o, d, tmin=0.001, tmax=INF):
+    """Returns (t, object index, order path) of the reference's winner, or None."""
+
+    def hit_ref(ref, o, d):
+        ty, ix = ref >> A.REF_TYPE_SHIFT, ref & A.REF_INDEX_MASK
+        if ref == A.REF_NONE:
+            return None
+        if ty == A.REF_NODE:
+            nd = fs.nodes[ix]
+            res = None
+            for c in range(2):
+                cref = int(nd["child"][c])
+                if cref == A.REF_NONE:
+                    continue
+                if (cref >> A.REF_TYPE_SHIFT) == A.REF_NODE:
+                    lo, hi = fs.child_boxes[ix, c, 0], fs.child_boxes[ix, c, 1]
+                    if not box_hit(lo, hi, o, d, tmin, tmax):
+                        continue
+                h = hit_ref(cref, o, d)
+                if h is not None and (res is None or not (res[0] < h[0])):  # ties -> right (later) child
+                    res = h
+            return res
+        if ty == A.REF_SPHERE:
+            c, r = fs.sc[ix], fs.sr[ix]
+            ec = (c[0] - o[0], c[1] - o[1], c[2] - o[2])
+            a, h = _dot(d, d), _dot(ec, d)
+            cc = _dot(ec, ec) - r * r
+            disc = h * h - a * cc
+            if disc != disc or disc < 0.0:
+                return None
+            sq = math.sqrt(disc)
+            t = _div(h - sq, a)
+            if not (tmin < t < tmax):
+                t = _div(h + sq, a)
+                if not (tmin < t < tmax):
+                    return None
+            return (t, int(fs.sobj[ix]))
+        if ty == A.REF_PLANE:
+            n = fs.pn[ix]
+            denom = _dot(n, d)
+            if abs(denom) < 1e-8:
+                return None
+            t = _div(fs.pd[ix] - _dot(n, o), denom)
+            if not (tmin <= t <= tmax):
+                return None
+            p = [o[k] + t * d[k] for k in range(3)]
+            q = [p[k] - fs.pp[ix][k] for k in range(3)]
+            alpha, beta = _dot(fs.pw[ix], _cross(q, fs.pv[ix])), _dot(fs.pw[ix], _cross(fs.pu[ix], q))
+            if fs.pm[ix] & 0x80000000:
+                ok = alpha > 0.0 and beta > 0.0 and (alpha + beta) < 1.0
+            else:
+                ok = 0.0 <= alpha <= 1.0 and 0.0 <= beta <= 1.0
+            return (t, int(fs.pobj[ix])) if ok else None
+        if ty == A.REF_INSTANCE:
+            ins = fs.inst[ix]
+            oo, dd = list(o), list(d)
+            for k in range(ins.n_xforms):
+                x = fs.xf[ins.first_xform + k]
+                m = list(x.to_obj)
+                if x.kind == 0:
+                    oo = [oo[i] - m[i] for i in range(3)]
+                elif x.kind == 1:
+                    oo, dd = _mat3(m, oo), _mat3(m, dd)
+                else:
+                    oo, dd = _mat4(m, oo, True), _mat4(m, dd, False)
+            inner = ins.inner
+            if inner == A.REF_NONE:
+                return None
+            if (inner >> A.REF_TYPE_SHIFT) == A.REF_NODE:
+                if not box_hit(list(ins.inner_box.lo), list(ins.inner_box.hi), oo, dd, tmin, tmax):
+                    return None
+            return hit_ref(inner, oo, dd)
+        return None
+
+    root = fs.root
+    if root != A.REF_NONE and (root >> A.REF_TYPE_SHIFT) == A.REF_NODE:
+        if not box_hit(fs.root_box[0], fs.root_box[1], o, d, tmin, tmax):
+            return None
+    return hit_ref(root, list(o), list(d))

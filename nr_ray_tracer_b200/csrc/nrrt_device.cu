@@ -24,11 +24,20 @@
 #define NRRT_BLOCK 128
 
 // =========================================================================== kernels
+// Work decomposition.  A work item is (owned pixel, sample chunk): the pixel's samples
+// [c*chunk, min((c+1)*chunk, spp)).  Items are numbered chunk-major (item = c * n_owned_pixels + pixel) and handed
+// out dynamically from one global counter, so every path slot stays busy until the whole image is done no matter
+// how uneven the per-pixel path lengths are.  A slot traces its item's samples one after the other, sums their
+// radiance in f64 in sample order, writes that partial sum to partials[item] and grabs the next item.
+// k_resolve adds a pixel's partials in chunk order: the result does not depend on scheduling, slot count or the
+// number of GPUs (chunk size depends on spp only).
 struct RenderParams {
     uint2 key;               // Philox key
     uint32_t n_owned_pixels; // pixels rendered by this context
-    uint32_t lanes;          // sample lanes per pixel: lane l renders samples l, l+lanes, ...
-    uint32_t n_work;         // n_owned_pixels * lanes
+    uint32_t chunk;          // samples per work item
+    uint32_t n_chunks;       // ceil(spp / chunk)
+    uint32_t n_items;        // n_owned_pixels * n_chunks
+    uint32_t n_slots;        // paths in flight
     uint32_t rank, world, rows_per_block;
 };
 
@@ -40,6 +49,20 @@ __device__ __forceinline__ void owned_pixel(const nrrt_camera& cam, const Render
     x = po - j * W;
     uint32_t b = j / P.rows_per_block, r = j - b * P.rows_per_block;
     y = (b * P.world + P.rank) * P.rows_per_block + r;
+}
+
+struct WorkItem {
+    uint32_t x, y;        // pixel
+    uint32_t sample_end;  // one past the last sample of the chunk
+};
+// item -> pixel + sample range; returns the first sample
+__device__ __forceinline__ uint32_t decode_item(const nrrt_camera& cam, const RenderParams& P, uint32_t item,
+                                                WorkItem& wi) {
+    uint32_t c = item / P.n_owned_pixels, po = item - c * P.n_owned_pixels;
+    owned_pixel(cam, P, po, wi.x, wi.y);
+    uint32_t first = c * P.chunk;
+    wi.sample_end = min(first + P.chunk, cam.samples_per_pixel);
+    return first;
 }
 
 template <bool VISIT_ALL, bool COUNT>
@@ -109,28 +132,35 @@ __device__ __forceinline__ bool path_step(const DevScene& S, const nrrt_camera& 
     return bounce < cam.ray_max_bounces;  // camera.rs:276-278
 }
 
+// Megakernel variant: persistent threads, whole path state in registers.
+//   counters: [0]=segments [1]=paths [2..4]=node/exact/prim counts (COUNT) [5]=next work item
 template <bool COUNT>
 __global__ void __launch_bounds__(NRRT_BLOCK)
 k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_camera cam,
-              const __grid_constant__ RenderParams P, double* __restrict__ acc, unsigned long long* __restrict__ counters) {
+              const __grid_constant__ RenderParams P, double* __restrict__ partials,
+              unsigned long long* __restrict__ counters) {
     extern __shared__ uint32_t s_stack[];
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long segs = 0, paths = 0;
     TraceCounters tc{0, 0, 0};
-    if (w < P.n_work) {
-        uint32_t lane = w / P.n_owned_pixels, po = w - lane * P.n_owned_pixels;
-        uint32_t x, y;
-        owned_pixel(cam, P, po, x, y);
-        Sampler smp{P.key, y * cam.width + x, lane};
-        const uint32_t spp = cam.samples_per_pixel;
+    if (w < P.n_slots) {
+        uint32_t item = w;  // the first n_slots items are pre-assigned; the counter starts at n_slots
+        WorkItem wi;
+        Sampler smp{P.key, 0u, 0u};
         d3 sum = mk3(0.0, 0.0, 0.0);
         d3 o, d, T, L;
         uint32_t bounce = 0;
-        bool alive = false;
+        bool alive = false, have_item = false;
         for (;;) {
-            if (!alive) {  // regenerate: next sample of this lane
-                if (smp.sample >= spp) break;
-                camera_ray(cam, x, y, smp, o, d);
+            if (!alive) {
+                if (!have_item) {
+                    if (item >= P.n_items) break;
+                    smp.sample = decode_item(cam, P, item, wi);
+                    smp.pixel = wi.y * cam.width + wi.x;
+                    sum = mk3(0.0, 0.0, 0.0);
+                    have_item = true;
+                }
+                camera_ray(cam, wi.x, wi.y, smp, o, d);
                 T = mk3(1.0, 1.0, 1.0);
                 L = mk3(0.0, 0.0, 0.0);
                 bounce = 0;
@@ -143,11 +173,14 @@ k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
             alive = path_step(S, cam, h, smp, o, d, T, L, bounce);
             if (!alive) {
                 sum = add3(sum, L);
-                smp.sample += P.lanes;
+                if (++smp.sample >= wi.sample_end) {  // chunk done: publish its partial sum, fetch the next item
+                    size_t base = (size_t)item * 3;
+                    partials[base] = sum.x, partials[base + 1] = sum.y, partials[base + 2] = sum.z;
+                    item = (uint32_t)atomicAdd(&counters[5], 1ull);
+                    have_item = false;
+                }
             }
         }
-        size_t base = (size_t)w * 3;
-        acc[base] = sum.x, acc[base + 1] = sum.y, acc[base + 2] = sum.z;
     }
     // block-level reduction of the counters
     __shared__ unsigned long long s_cnt[2];
@@ -173,30 +206,33 @@ k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
     }
 }
 
-// sum the lanes of every owned pixel in lane order, divide by spp, cast to f32 (camera.rs:331-337)
+// per-pixel sample accumulation: add the chunk partials in chunk order, divide by spp, cast to f32
+// (camera.rs:329-337)
 __global__ void k_resolve(const __grid_constant__ nrrt_camera cam, const __grid_constant__ RenderParams P,
-                          const double* __restrict__ acc, float* __restrict__ out) {
+                          const double* __restrict__ partials, float* __restrict__ out) {
     uint32_t po = blockIdx.x * blockDim.x + threadIdx.x;
     if (po >= P.n_owned_pixels) return;
     d3 s = mk3(0.0, 0.0, 0.0);
-    for (uint32_t l = 0; l < P.lanes; ++l) {
-        size_t b = ((size_t)l * P.n_owned_pixels + po) * 3;
-        s = add3(s, mk3(acc[b], acc[b + 1], acc[b + 2]));
+    for (uint32_t c = 0; c < P.n_chunks; ++c) {
+        size_t b = ((size_t)c * P.n_owned_pixels + po) * 3;
+        s = add3(s, mk3(partials[b], partials[b + 1], partials[b + 2]));
     }
-    d3 c = div3(s, (double)cam.samples_per_pixel);
+    d3 col = div3(s, (double)cam.samples_per_pixel);
     uint32_t x, y;
     owned_pixel(cam, P, po, x, y);
     size_t ob = ((size_t)y * cam.width + x) * 3;
-    out[ob] = (float)c.x, out[ob + 1] = (float)c.y, out[ob + 2] = (float)c.z;
+    out[ob] = (float)col.x, out[ob + 1] = (float)col.y, out[ob + 2] = (float)col.z;
 }
 
 // ------------------------------------------------------------------ wavefront
-// SoA path state, one slot per (lane, owned pixel).  All arrays have n_work entries per component.
+// SoA path state, one entry per slot (n = n_slots).
 struct WfState {
-    double* ray;    // [6][n]: ox oy oz dx dy dz
-    double* T;      // [3][n]
-    double* L;      // [3][n]
-    double* acc;    // [n][3] (same layout k_resolve reads)
+    double* ray;       // [6][n]: ox oy oz dx dy dz
+    double* T;         // [3][n] throughput.  (The radiance of a LIVE path is identically zero: no reference
+                       //        material both emits and scatters — material.rs:10-27, diffuse_light.rs — so it
+                       //        is not stored; a path contributes T*background or T*emitted when it ends.)
+    double* sum;       // [3][n] running partial sum of the slot's current work item
+    uint32_t* item;    // [n] current work item
     uint32_t* sample;  // [n] current sample index
     uint32_t* bounce;  // [n]
     double* hit_t;     // [n]
@@ -204,40 +240,41 @@ struct WfState {
     uint32_t* hit_inst;   // [1 + MAX_DEPTH][n]: depth, inst[0..]
     uint32_t* queue[2];   // [n] slot indices
     uint32_t* count;      // [2] queue lengths
-    unsigned long long* counters;  // [0]=segments [1]=paths
+    double* partials;     // [n_items][3]
+    unsigned long long* counters;  // [0]=segments [1]=paths [5]=next work item
 };
 
+// ray generation for the initial items
 __global__ void __launch_bounds__(NRRT_BLOCK)
 k_wf_init(const __grid_constant__ nrrt_camera cam, const __grid_constant__ RenderParams P,
           const __grid_constant__ WfState W) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w == 0) {
-        W.count[0] = P.n_work;
+        W.count[0] = P.n_slots;
         W.count[1] = 0;
-        W.counters[1] += P.n_work;
+        W.counters[1] += P.n_slots;
     }
-    if (w >= P.n_work) return;
-    uint32_t n = P.n_work;
-    uint32_t lane = w / P.n_owned_pixels, po = w - lane * P.n_owned_pixels;
-    uint32_t x, y;
-    owned_pixel(cam, P, po, x, y);
-    Sampler smp{P.key, y * cam.width + x, lane};
+    if (w >= P.n_slots) return;
+    uint32_t n = P.n_slots;
+    WorkItem wi;
+    uint32_t first = decode_item(cam, P, w, wi);
+    Sampler smp{P.key, wi.y * cam.width + wi.x, first};
     d3 o, d;
-    camera_ray(cam, x, y, smp, o, d);
+    camera_ray(cam, wi.x, wi.y, smp, o, d);
     W.ray[0 * (size_t)n + w] = o.x, W.ray[1 * (size_t)n + w] = o.y, W.ray[2 * (size_t)n + w] = o.z;
     W.ray[3 * (size_t)n + w] = d.x, W.ray[4 * (size_t)n + w] = d.y, W.ray[5 * (size_t)n + w] = d.z;
     for (int c = 0; c < 3; ++c) {
         W.T[c * (size_t)n + w] = 1.0;
-        W.L[c * (size_t)n + w] = 0.0;
-        W.acc[(size_t)w * 3 + c] = 0.0;
+        W.sum[c * (size_t)n + w] = 0.0;
     }
-    W.sample[w] = lane;
+    W.item[w] = w;
+    W.sample[w] = first;
     W.bounce[w] = 0;
     W.queue[0][w] = w;
 }
 
 // traverse / intersect: closest hit for every queued ray
-__global__ void __launch_bounds__(NRRT_BLOCK)
+__global__ void __launch_bounds__(NRRT_BLOCK, 4)
 k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState W, uint32_t n, uint32_t qin) {
     extern __shared__ uint32_t s_stack[];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,27 +292,31 @@ k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState 
     for (uint32_t l = 0; l < h.depth; ++l) W.hit_inst[(size_t)(1 + l) * n + slot] = h.inst[l];
 }
 
-// shade / scatter, path regeneration, warp-ballot compaction of the survivors into the other queue
+// shade / scatter, in-slot path regeneration, dynamic work fetch, warp-ballot compaction of the survivors
 __global__ void __launch_bounds__(NRRT_BLOCK)
 k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_camera cam,
            const __grid_constant__ RenderParams P, const __grid_constant__ WfState W, uint32_t qin) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n = P.n_work;
-    uint32_t n_in = W.count[qin];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = P.n_slots;
+    const uint32_t n_in = W.count[qin];
+    const uint32_t lane_id = threadIdx.x & 31u;
     if (i == 0) W.counters[0] += n_in;  // one closest-hit query per queued ray
-    bool survive = false;
-    uint32_t slot = 0;
-    if (i < n_in) {
+    bool active = i < n_in, survive = false, need_item = false, new_path = false;
+    uint32_t slot = 0, item = 0, bounce = 0;
+    d3 o, d, T, L, sum;
+    Sampler smp{P.key, 0u, 0u};
+    WorkItem wi;
+    if (active) {
         slot = W.queue[qin][i];
-        d3 o = mk3(W.ray[slot], W.ray[(size_t)n + slot], W.ray[2 * (size_t)n + slot]);
-        d3 d = mk3(W.ray[3 * (size_t)n + slot], W.ray[4 * (size_t)n + slot], W.ray[5 * (size_t)n + slot]);
-        d3 T = mk3(W.T[slot], W.T[(size_t)n + slot], W.T[2 * (size_t)n + slot]);
-        d3 L = mk3(W.L[slot], W.L[(size_t)n + slot], W.L[2 * (size_t)n + slot]);
-        uint32_t bounce = W.bounce[slot];
-        uint32_t lane = slot / P.n_owned_pixels, po = slot - lane * P.n_owned_pixels;
-        uint32_t x, y;
-        owned_pixel(cam, P, po, x, y);
-        Sampler smp{P.key, y * cam.width + x, W.sample[slot]};
+        o = mk3(W.ray[slot], W.ray[(size_t)n + slot], W.ray[2 * (size_t)n + slot]);
+        d = mk3(W.ray[3 * (size_t)n + slot], W.ray[4 * (size_t)n + slot], W.ray[5 * (size_t)n + slot]);
+        T = mk3(W.T[slot], W.T[(size_t)n + slot], W.T[2 * (size_t)n + slot]);
+        L = mk3(0.0, 0.0, 0.0);
+        bounce = W.bounce[slot];
+        item = W.item[slot];
+        decode_item(cam, P, item, wi);
+        smp.pixel = wi.y * cam.width + wi.x;
+        smp.sample = W.sample[slot];
         HitId h;
         h.t = W.hit_t[slot];
         h.prim = W.hit_prim[slot];
@@ -283,36 +324,58 @@ k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_came
 #pragma unroll
         for (uint32_t l = 0; l < NRRT_MAX_INSTANCE_DEPTH; ++l)
             h.inst[l] = (l < h.depth) ? W.hit_inst[(size_t)(1 + l) * n + slot] : 0u;
-        bool alive = path_step(S, cam, h, smp, o, d, T, L, bounce);
-        if (!alive) {  // path finished: accumulate, then regenerate the lane's next sample in place
-            size_t ab = (size_t)slot * 3;
-            W.acc[ab] = xadd(W.acc[ab], L.x);
-            W.acc[ab + 1] = xadd(W.acc[ab + 1], L.y);
-            W.acc[ab + 2] = xadd(W.acc[ab + 2], L.z);
-            smp.sample += P.lanes;
-            if (smp.sample < cam.samples_per_pixel) {
-                camera_ray(cam, x, y, smp, o, d);
-                T = mk3(1.0, 1.0, 1.0);
-                L = mk3(0.0, 0.0, 0.0);
-                bounce = 0;
-                alive = true;
-                W.sample[slot] = smp.sample;
-                atomicAdd(&W.counters[1], 1ull);
+        survive = path_step(S, cam, h, smp, o, d, T, L, bounce);
+        if (!survive) {  // path finished: add it to the item's partial sum (sample order)
+            sum = add3(mk3(W.sum[slot], W.sum[(size_t)n + slot], W.sum[2 * (size_t)n + slot]), L);
+            ++smp.sample;
+            if (smp.sample >= wi.sample_end) {  // item finished: publish, then fetch another below
+                size_t pb = (size_t)item * 3;
+                W.partials[pb] = sum.x, W.partials[pb + 1] = sum.y, W.partials[pb + 2] = sum.z;
+                sum = mk3(0.0, 0.0, 0.0);
+                need_item = true;
+            } else {
+                new_path = true;
             }
         }
-        if (alive) {
-            W.ray[slot] = o.x, W.ray[(size_t)n + slot] = o.y, W.ray[2 * (size_t)n + slot] = o.z;
-            W.ray[3 * (size_t)n + slot] = d.x, W.ray[4 * (size_t)n + slot] = d.y, W.ray[5 * (size_t)n + slot] = d.z;
-            W.T[slot] = T.x, W.T[(size_t)n + slot] = T.y, W.T[2 * (size_t)n + slot] = T.z;
-            W.L[slot] = L.x, W.L[(size_t)n + slot] = L.y, W.L[2 * (size_t)n + slot] = L.z;
-            W.bounce[slot] = bounce;
-        }
-        survive = alive;
     }
-    // warp-aggregated compaction
+    // warp-aggregated fetch from the global work counter
+    unsigned need = __ballot_sync(0xffffffffu, need_item);
+    if (need) {
+        uint32_t leader = __ffs(need) - 1, base = 0;
+        if (lane_id == leader) base = (uint32_t)atomicAdd(&W.counters[5], (unsigned long long)__popc(need));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (need_item) {
+            item = base + __popc(need & ((1u << lane_id) - 1u));
+            if (item < P.n_items) {
+                smp.sample = decode_item(cam, P, item, wi);
+                smp.pixel = wi.y * cam.width + wi.x;
+                W.item[slot] = item;
+                new_path = true;
+            }
+        }
+    }
+    if (active && !survive) {
+        W.sum[slot] = sum.x, W.sum[(size_t)n + slot] = sum.y, W.sum[2 * (size_t)n + slot] = sum.z;
+        if (new_path) {  // regenerate in place: next sample of the item
+            camera_ray(cam, wi.x, wi.y, smp, o, d);
+            T = mk3(1.0, 1.0, 1.0);
+            L = mk3(0.0, 0.0, 0.0);
+            bounce = 0;
+            survive = true;
+            W.sample[slot] = smp.sample;
+        }
+    }
+    unsigned born = __ballot_sync(0xffffffffu, new_path);
+    if (born && lane_id == 0) atomicAdd(&W.counters[1], (unsigned long long)__popc(born));
+    if (survive) {
+        W.ray[slot] = o.x, W.ray[(size_t)n + slot] = o.y, W.ray[2 * (size_t)n + slot] = o.z;
+        W.ray[3 * (size_t)n + slot] = d.x, W.ray[4 * (size_t)n + slot] = d.y, W.ray[5 * (size_t)n + slot] = d.z;
+        W.T[slot] = T.x, W.T[(size_t)n + slot] = T.y, W.T[2 * (size_t)n + slot] = T.z;
+        W.bounce[slot] = bounce;
+    }
+    // warp-aggregated compaction of the survivors into the other queue
     unsigned ballot = __ballot_sync(0xffffffffu, survive);
     if (ballot) {
-        uint32_t lane_id = threadIdx.x & 31u;
         uint32_t base = 0;
         if (lane_id == 0) base = atomicAdd(&W.count[qin ^ 1], (uint32_t)__popc(ballot));
         base = __shfl_sync(0xffffffffu, base, 0);
@@ -707,19 +770,24 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     P.key = make_uint2((uint32_t)o.seed, (uint32_t)(o.seed >> 32));
     P.rank = o.rank, P.world = o.world, P.rows_per_block = o.rows_per_block;
     P.n_owned_pixels = owned_rows(H, o.rank, o.world, o.rows_per_block) * W;
-    // sample lanes: keep >= ~1M paths in flight; depends on the full image only, so the per-pixel sum
-    // order (and the image, bit for bit) is the same for every GPU count
-    uint32_t lanes = 1;
-    const uint64_t target = o.max_slots ? o.max_slots : (1ull << 20);
-    while ((uint64_t)lanes * total_pixels < target && lanes * 2 <= c.samples_per_pixel) lanes *= 2;
-    P.lanes = lanes;
-    P.n_work = P.n_owned_pixels * lanes;
+    // chunking depends on spp only (=> the per-pixel sum order, and the image bit for bit, are the same for
+    // every slot count and GPU count): at most 32 chunks per pixel
+    P.chunk = (c.samples_per_pixel + 31) / 32;
+    P.n_chunks = (c.samples_per_pixel + P.chunk - 1) / P.chunk;
+    const uint64_t n_items64 = (uint64_t)P.n_owned_pixels * P.n_chunks;
+    if (n_items64 > 0xFFFFFFF0ull) {
+        ctx->err = "too many work items";
+        return NRRT_ERR_LIMIT;
+    }
+    P.n_items = (uint32_t)n_items64;
+    const uint32_t want_slots = o.max_slots ? o.max_slots : (1u << 20);
+    P.n_slots = (uint32_t)std::min<uint64_t>(n_items64, want_slots);
 
     const bool out_dev = (o.flags & NRRT_RENDER_OUT_DEVICE) != 0;
-    const size_t fb_bytes = (size_t)total_pixels * 3 * sizeof(float);
-    const size_t n = P.n_work;
     const bool counting = (o.flags & NRRT_RENDER_COUNT) != 0;
     const bool wavefront = o.mode == NRRT_MODE_WAVEFRONT && !counting;
+    const size_t fb_bytes = (size_t)total_pixels * 3 * sizeof(float);
+    const size_t n = P.n_slots;
     // scratch layout
     size_t off = 0;
     auto carve = [&](size_t bytes) {
@@ -728,13 +796,14 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         return at;
     };
     size_t o_fb = out_dev ? 0 : carve(fb_bytes);
-    size_t o_acc = carve(n * 3 * sizeof(double));
-    size_t o_ray = 0, o_T = 0, o_L = 0, o_sample = 0, o_bounce = 0, o_ht = 0, o_hp = 0, o_hi = 0, o_q0 = 0, o_q1 = 0,
-           o_cnt = 0;
+    size_t o_part = carve((size_t)P.n_items * 3 * sizeof(double));
+    size_t o_ray = 0, o_T = 0, o_sum = 0, o_item = 0, o_sample = 0, o_bounce = 0, o_ht = 0, o_hp = 0, o_hi = 0,
+           o_q0 = 0, o_q1 = 0, o_cnt = 0;
     if (wavefront) {
         o_ray = carve(n * 6 * sizeof(double));
         o_T = carve(n * 3 * sizeof(double));
-        o_L = carve(n * 3 * sizeof(double));
+        o_sum = carve(n * 3 * sizeof(double));
+        o_item = carve(n * sizeof(uint32_t));
         o_sample = carve(n * sizeof(uint32_t));
         o_bounce = carve(n * sizeof(uint32_t));
         o_ht = carve(n * sizeof(double));
@@ -748,9 +817,11 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     if (rc != NRRT_OK) return rc;
     char* base = (char*)ctx->scratch;
     float* d_fb = out_dev ? out_rgb : (float*)(base + o_fb);
-    double* d_acc = (double*)(base + o_acc);
+    double* d_part = (double*)(base + o_part);
 
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    // counters: [0] segments [1] paths [2..4] instrumentation [5] next work item (first n_slots pre-assigned)
+    unsigned long long init_counters[8] = {0, 0, 0, 0, 0, P.n_slots, 0, 0};
+    CK(cudaMemcpyAsync(ctx->d_counters, init_counters, sizeof init_counters, cudaMemcpyHostToDevice, ctx->stream));
     uint64_t launches = 0, extend_launches = 0;
     double extend_ms = 0.0;
     const size_t smem = (size_t)NRRT_BLOCK * NRRT_STACK_CAP * sizeof(uint32_t);
@@ -758,20 +829,20 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (n == 0 || c.ray_max_bounces == 0) {
         // nothing owned, or every path returns black at depth 0 (camera.rs:276-278)
-        if (n) CK(cudaMemsetAsync(d_acc, 0, n * 3 * sizeof(double), ctx->stream));
+        if (P.n_items) CK(cudaMemsetAsync(d_part, 0, (size_t)P.n_items * 3 * sizeof(double), ctx->stream));
     } else if (!wavefront) {
         if (counting)
-            k_render_mega<true><<<work_blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, c, P, d_acc, ctx->d_counters);
+            k_render_mega<true><<<work_blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, c, P, d_part, ctx->d_counters);
         else
-            k_render_mega<false><<<work_blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, c, P, d_acc, ctx->d_counters);
+            k_render_mega<false><<<work_blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, c, P, d_part, ctx->d_counters);
         CK(cudaGetLastError());
         ++launches;
     } else {
         WfState Wf;
         Wf.ray = (double*)(base + o_ray);
         Wf.T = (double*)(base + o_T);
-        Wf.L = (double*)(base + o_L);
-        Wf.acc = d_acc;
+        Wf.sum = (double*)(base + o_sum);
+        Wf.item = (uint32_t*)(base + o_item);
         Wf.sample = (uint32_t*)(base + o_sample);
         Wf.bounce = (uint32_t*)(base + o_bounce);
         Wf.hit_t = (double*)(base + o_ht);
@@ -780,36 +851,39 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         Wf.queue[0] = (uint32_t*)(base + o_q0);
         Wf.queue[1] = (uint32_t*)(base + o_q1);
         Wf.count = (uint32_t*)(base + o_cnt);
+        Wf.partials = d_part;
         Wf.counters = ctx->d_counters;
         k_wf_init<<<work_blocks, NRRT_BLOCK, 0, ctx->stream>>>(c, P, Wf);
         CK(cudaGetLastError());
         ++launches;
         // the queue length lives on the device; the host polls it through a pinned ring without stalling
-        const int RING = 32, POLL_EVERY = 8;
-        while (ctx->ev_pool.size() < (size_t)RING + 2 * 64) {
+        const int RING = 32, POLL_EVERY = 8, MAX_TIMED = 256;
+        while (ctx->ev_pool.size() < (size_t)RING + 2 * MAX_TIMED) {
             cudaEvent_t e;
             CK(cudaEventCreate(&e));
             ctx->ev_pool.push_back(e);
         }
         for (int k = 0; k < RING; ++k) ctx->h_count[k] = 0xFFFFFFFFu;
         uint64_t iter = 0, polls_issued = 0, polls_seen = 0;
+        // expected iteration count, to spread the timed extend launches over the whole render
+        const uint64_t expect_iters = std::max<uint64_t>(1, (uint64_t)P.n_items * P.chunk * 4 / std::max<uint32_t>(P.n_slots, 1u));
+        const uint64_t time_every = std::max<uint64_t>(1, expect_iters / MAX_TIMED);
         std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
-        int timing_used = 0;
         bool done = false;
         uint32_t qin = 0;
-        const uint64_t hard_cap = ((uint64_t)(c.samples_per_pixel + lanes - 1) / lanes) * c.ray_max_bounces + 8;
+        const uint64_t hard_cap = ((uint64_t)P.n_items * P.chunk / std::max<uint32_t>(P.n_slots, 1u) + P.chunk + 2) *
+                                      (uint64_t)c.ray_max_bounces + 64;
         while (!done && iter < hard_cap) {
-            bool timed = (iter % 16 == 0) && timing_used < 64;
+            bool timed = (iter % time_every == 0) && (int)timing.size() < MAX_TIMED;
             cudaEvent_t ta = nullptr, tb = nullptr;
             if (timed) {
-                ta = ctx->ev_pool[RING + 2 * timing_used], tb = ctx->ev_pool[RING + 2 * timing_used + 1];
+                ta = ctx->ev_pool[RING + 2 * timing.size()], tb = ctx->ev_pool[RING + 2 * timing.size() + 1];
                 CK(cudaEventRecord(ta, ctx->stream));
             }
             k_wf_extend<<<work_blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, Wf, (uint32_t)n, qin);
             if (timed) {
                 CK(cudaEventRecord(tb, ctx->stream));
                 timing.emplace_back(ta, tb);
-                ++timing_used;
             }
             k_wf_shade<<<work_blocks, NRRT_BLOCK, 0, ctx->stream>>>(ctx->dev, c, P, Wf, qin);
             CK(cudaGetLastError());
@@ -853,7 +927,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         if (!timing.empty()) extend_ms = sampled / (double)timing.size() * (double)extend_launches;
     }
     if (P.n_owned_pixels) {
-        k_resolve<<<(P.n_owned_pixels + 255) / 256, 256, 0, ctx->stream>>>(c, P, d_acc, d_fb);
+        k_resolve<<<(P.n_owned_pixels + 255) / 256, 256, 0, ctx->stream>>>(c, P, d_part, d_fb);
         CK(cudaGetLastError());
         ++launches;
     }

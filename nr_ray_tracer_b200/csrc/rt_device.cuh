@@ -275,14 +275,33 @@ __device__ __forceinline__ void box_filter(const Ray32& r, float lx, float ly, f
     m = fmaf(NRRT_BOX_EPS, fmaxf(fabsf(lo), fabsf(hi)), r.margin);
 }
 
+// Box test of a BVH *root* (scene root / nested BVH behind an instance; object.rs:102): f32 filter on the
+// on-the-fly rounded box first, the reference's exact f64 slab test only when the filter is inconclusive.
+template <bool COUNT>
+__device__ __forceinline__ bool root_box_test(const nrrt_box* b, const Ray32& r32, d3 o, d3 d, double tmin,
+                                              double tmax, float tmin32, float tmax32, TraceCounters* cnt) {
+    if (!r32.degenerate) {
+        float e, g, m;
+        box_filter(r32, (float)b->lo[0], (float)b->lo[1], (float)b->lo[2], (float)b->hi[0], (float)b->hi[1],
+                   (float)b->hi[2], tmin32, tmax32, e, g, m);
+        if (g >= m) return true;
+        if (g < -m) return false;
+    }
+    if (COUNT) cnt->exact++;
+    return box_hit_exact(b, o, d, tmin, tmax);
+}
+
 // BVH::hit (objects/object.rs:89-121) over the flattened scene.
 //   VISIT_ALL = true : visits exactly the reference's node set (no pruning by the best hit so far)
 //   VISIT_ALL = false: near-first order + conservative pruning by the best t (same result, fewer visits)
 // `stack` is this thread's slice of shared memory, stride `sstride` (bank-conflict free).
+//
+// Loop shape ("while-while"): the inner loop walks inner nodes only — cheap f32 work every lane of the warp can do
+// in lock step — until the lane holds a leaf; leaves (exact f64 primitive tests, instance entry/exit) are then
+// processed together, so the expensive divergent part runs once per round instead of once per node step.
 template <bool VISIT_ALL, bool COUNT>
 __device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, double tmin, double tmax,
-                                              volatile uint32_t* stack, uint32_t sstride, HitId& best,
-                                              TraceCounters* cnt) {
+                                              uint32_t* stack, uint32_t sstride, HitId& best, TraceCounters* cnt) {
     best.t = NRRT_INF;
     best.prim = NRRT_REF_NONE;
     best.depth = 0;
@@ -294,7 +313,8 @@ __device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, d
     for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) cur_inst[k] = 0;
     uint32_t level = 0;
     d3 o = wo, d = wd;
-    Ray32 r32 = make_ray32(o, d);
+    const Ray32 w32 = make_ray32(wo, wd);
+    Ray32 r32 = w32;
     const float tmin32 = (float)tmin;                              // filter bounds; margins cover the rounding
     const float tmax32 = (tmax < 3.0e38) ? (float)tmax : 3.4e38f;
     float tcull = 3.4e38f;                                         // f32 upper bound of best.t (+ slack)
@@ -302,15 +322,13 @@ __device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, d
     uint32_t sp = 0;
     uint32_t cur = S.root;
     // root of the scene: an inner node tests its own box (object.rs:102)
-    if (NRRT_REF_TYPE(cur) == NRRT_REF_NODE) {
-        if (COUNT) cnt->exact++;
-        if (!box_hit_exact(&S.root_box, o, d, tmin, tmax)) cur = NRRT_REF_NONE;
-    }
+    if (NRRT_REF_TYPE(cur) == NRRT_REF_NODE &&
+        !root_box_test<COUNT>(&S.root_box, r32, o, d, tmin, tmax, tmin32, tmax32, cnt))
+        cur = NRRT_REF_NONE;
 
     for (;;) {
-        uint32_t ty = NRRT_REF_TYPE(cur);
-        if (ty == NRRT_REF_NODE) {
-            // ---- inner node: filter both child boxes
+        // ---------------- phase 1: inner nodes
+        while (NRRT_REF_TYPE(cur) == NRRT_REF_NODE) {
             uint32_t ni = NRRT_REF_INDEX(cur);
             const float4* np = S.nodes + 4 * (size_t)ni;
             float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
@@ -320,14 +338,13 @@ __device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, d
             float e0, g0, m0, e1, g1, m1;
             box_filter(r32, n0.x, n0.y, n0.z, n1.z, n1.w, n2.x, tmin32, tmax32, e0, g0, m0);
             box_filter(r32, n0.w, n1.x, n1.y, n2.y, n2.z, n2.w, tmin32, tmax32, e1, g1, m1);
-            bool v0, v1;
-            {
-                bool leaf0 = NRRT_REF_TYPE(c0) != NRRT_REF_NODE, leaf1 = NRRT_REF_TYPE(c1) != NRRT_REF_NODE;
-                // leaves are not box-tested by the reference (object.rs:95-97): visit unless certainly missed
-                v0 = (c0 != NRRT_REF_NONE) && (r32.degenerate || !(g0 < -m0));
-                v1 = (c1 != NRRT_REF_NONE) && (r32.degenerate || !(g1 < -m1));
-                bool amb0 = v0 && !leaf0 && (r32.degenerate || !(g0 >= m0));
-                bool amb1 = v1 && !leaf1 && (r32.degenerate || !(g1 >= m1));
+            // leaves are not box-tested by the reference (object.rs:95-97): visit unless certainly missed;
+            // inner children must pass the reference's test: certain from the filter, else exact
+            bool v0 = (c0 != NRRT_REF_NONE) && (r32.degenerate || !(g0 < -m0));
+            bool v1 = (c1 != NRRT_REF_NONE) && (r32.degenerate || !(g1 < -m1));
+            bool amb0 = v0 && NRRT_REF_TYPE(c0) == NRRT_REF_NODE && (r32.degenerate || !(g0 >= m0));
+            bool amb1 = v1 && NRRT_REF_TYPE(c1) == NRRT_REF_NODE && (r32.degenerate || !(g1 >= m1));
+            if (amb0 || amb1) {  // rare
                 if (amb0) {
                     if (COUNT) cnt->exact++;
                     v0 = box_hit_exact(S.child_boxes + 2 * (size_t)ni, o, d, tmin, tmax);
@@ -344,21 +361,22 @@ __device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, d
             }
             if (v0 && v1) {
                 bool swap = !VISIT_ALL && (e1 < e0);
-                uint32_t nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
-                stack[sp * sstride] = farc;
+                stack[sp * sstride] = swap ? c0 : c1;
                 ++sp;
-                cur = nearc;
-                continue;
+                cur = swap ? c1 : c0;
+            } else if (v0 || v1) {
+                cur = v0 ? c0 : c1;
+            } else {
+                cur = NRRT_REF_NONE;
+                if (sp) {
+                    --sp;
+                    cur = stack[sp * sstride];
+                }
             }
-            if (v0) {
-                cur = c0;
-                continue;
-            }
-            if (v1) {
-                cur = c1;
-                continue;
-            }
-        } else if (ty == NRRT_REF_SPHERE || ty == NRRT_REF_PLANE) {
+        }
+        // ---------------- phase 2: one leaf (primitive / instance / level marker), or nothing left
+        const uint32_t ty = NRRT_REF_TYPE(cur);
+        if (ty == NRRT_REF_SPHERE || ty == NRRT_REF_PLANE) {
             if (COUNT) cnt->prims++;
             double a_, b_;
             double t = (ty == NRRT_REF_SPHERE) ? sphere_t(S, NRRT_REF_INDEX(cur), o, d, tmin, tmax)
@@ -378,37 +396,40 @@ __device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, d
                 }
             }
         } else if (ty == NRRT_REF_INSTANCE) {
-            // ---- enter an instance: transform the ray, remember how to get back
+            // enter an instance: transform the ray (exactly, wrapper by wrapper), test the nested root's box
             uint32_t ii = NRRT_REF_INDEX(cur);
             const nrrt_instance* in = &S.instances[ii];
             uint32_t inner = in->inner;
             if (inner != NRRT_REF_NONE && level < NRRT_MAX_INSTANCE_DEPTH) {
                 d3 no = o, nd = d;
                 instance_ray(S, ii, no, nd);
+                Ray32 n32 = make_ray32(no, nd);
                 bool enter = true;
-                if (NRRT_REF_TYPE(inner) == NRRT_REF_NODE) {  // nested BVH root tests its own box
-                    if (COUNT) cnt->exact++;
-                    enter = box_hit_exact(&in->inner_box, no, nd, tmin, tmax);
-                }
+                if (NRRT_REF_TYPE(inner) == NRRT_REF_NODE)
+                    enter = root_box_test<COUNT>(&in->inner_box, n32, no, nd, tmin, tmax, tmin32, tmax32, cnt);
                 if (enter) {
                     stack[sp * sstride] = NRRT_REF_POP;
                     ++sp;
                     cur_inst[level] = ii;
                     ++level;
                     o = no, d = nd;
-                    r32 = make_ray32(o, d);
+                    r32 = n32;
                     cur = inner;
                     continue;
                 }
             }
         } else if (cur == NRRT_REF_POP) {
-            // ---- leave the instance: rebuild the parent-level ray from the world ray
+            // leave the instance: rebuild the parent-level ray from the world ray (bit-identical recomputation)
             --level;
             o = wo, d = wd;
-            for (uint32_t l = 0; l < level; ++l) instance_ray(S, cur_inst[l], o, d);
-            r32 = make_ray32(o, d);
+            if (level == 0) {
+                r32 = w32;
+            } else {
+                for (uint32_t l = 0; l < level; ++l) instance_ray(S, cur_inst[l], o, d);
+                r32 = make_ray32(o, d);
+            }
         }
-        // pop
+        // next
         if (sp == 0) break;
         --sp;
         cur = stack[sp * sstride];

@@ -156,7 +156,7 @@ def run_reference(args):
 def scene_h2d_bytes(desc) -> int:
     d = desc
     b = d.n_nodes * 64 + d.n_nodes * 2 * 48
-    b += d.n_spheres * (3 * 8 + 8 + 3 * 4) + d.n_planes * (5 * 3 * 8 + 8 + 3 * 4)
+    b += d.n_spheres * (32 + 3 * 4) + d.n_planes * (128 + 3 * 4)
     b += d.n_instances * (64 + 4) + d.n_xforms * 200 + d.n_materials * 16 + d.n_textures * 72
     for i in range(d.n_images):
         b += d.images[i].width * d.images[i].height * 4
@@ -284,7 +284,7 @@ def run_b200(args):
         prims_seg = cst["prim_tests"] / cst["segments"]
         exact_seg = cst["box_exact"] / cst["segments"]
         d = host.desc
-        b_prim = 132 if d.n_planes >= d.n_spheres else 36   # bytes one exact primitive test reads
+        b_prim = 128 if d.n_planes >= d.n_spheres else 32   # bytes one exact primitive test reads (one record)
         b_state = 48 + 24 + 4 if mode == A.MODE_WAVEFRONT else 0  # extend kernel: ray in, hit out, queue index
         bytes_seg = nodes_seg * 64 + exact_seg * 48 + prims_seg * b_prim + b_state
         peaks = {}

@@ -16,7 +16,7 @@
  *      materials, textures.  nrrt_host_build() runs the reference's BVH build
  *      (objects/object.rs:41-73) on the host and flattens the tree into ...
  *   2. "flat" layer   (nrrt_scene_desc) — the structure-of-arrays device layout
- *      (64-byte two-child f32 nodes + exact f64 boxes, primitive SoA, instance
+ *      (64-byte two-child f32 nodes + exact f64 boxes, aligned primitive records, instance
  *      transform chains, material/texture tables) that nrrt_scene_upload()
  *      copies to HBM and the CUDA kernels traverse.
  *
@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NRRT_ABI_VERSION 1
+#define NRRT_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------ */
 enum {
@@ -216,22 +216,18 @@ typedef struct nrrt_scene_desc {
     uint32_t root;               /* ref of Scene.objects                        */
     nrrt_box root_box;           /* its bbox when root is a NODE                */
 
-    /* spheres (SoA) */
+    /* spheres: one 32-byte record per sphere = {center.x, center.y, center.z, radius} (2 x LDG.128) */
     uint32_t n_spheres;
-    const double* sphere_center; /* [n][3] */
-    const double* sphere_radius; /* [n]    */
+    const double* sphere_rec;      /* [n][4] */
     const uint32_t* sphere_material;
     const uint32_t* sphere_order;  /* DFS leaf order (tie-break, object.rs:110-114) */
     const uint32_t* sphere_object; /* graph object index (reported in nrrt_hit.object) */
 
-    /* planes (SoA): p,u,v + the derived normal,d,w exactly as PlaneBuilder::build */
+    /* planes: one 128-byte record (= one cache line, 8 x LDG.128) per plane, everything Plane::hit reads, with
+     * normal, d, w derived exactly as PlaneBuilder::build does (plane.rs:109-114):
+     *   [0..2] normal  [3] d  [4..6] p  [7..9] w  [10..12] u  [13..15] v */
     uint32_t n_planes;
-    const double* plane_p;      /* [n][3] */
-    const double* plane_u;      /* [n][3] */
-    const double* plane_v;      /* [n][3] */
-    const double* plane_normal; /* [n][3] */
-    const double* plane_w;      /* [n][3] */
-    const double* plane_d;      /* [n]    */
+    const double* plane_rec;        /* [n][16] */
     const uint32_t* plane_material; /* bit 31 set = Triangle, else Quad */
     const uint32_t* plane_order;
     const uint32_t* plane_object;

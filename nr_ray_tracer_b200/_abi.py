@@ -5,7 +5,7 @@ struct sizes against the values the compiled library reports.
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # status codes
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NO_SCENE, ERR_LIMIT, ERR_IO = 0, -1, -2, -3, -4, -5, -6
@@ -90,10 +90,9 @@ class SceneDesc(C.Structure):
         ("abi_version", u32),
         ("n_nodes", u32), ("nodes", C.POINTER(Node)), ("child_boxes", C.POINTER(Box)),
         ("root", u32), ("root_box", Box),
-        ("n_spheres", u32), ("sphere_center", C.POINTER(f64)), ("sphere_radius", C.POINTER(f64)),
+        ("n_spheres", u32), ("sphere_rec", C.POINTER(f64)),
         ("sphere_material", C.POINTER(u32)), ("sphere_order", C.POINTER(u32)), ("sphere_object", C.POINTER(u32)),
-        ("n_planes", u32), ("plane_p", C.POINTER(f64)), ("plane_u", C.POINTER(f64)), ("plane_v", C.POINTER(f64)),
-        ("plane_normal", C.POINTER(f64)), ("plane_w", C.POINTER(f64)), ("plane_d", C.POINTER(f64)),
+        ("n_planes", u32), ("plane_rec", C.POINTER(f64)),
         ("plane_material", C.POINTER(u32)), ("plane_order", C.POINTER(u32)), ("plane_object", C.POINTER(u32)),
         ("n_instances", u32), ("instances", C.POINTER(Instance)), ("instance_order", C.POINTER(u32)),
         ("n_xforms", u32), ("xforms", C.POINTER(Xform)),

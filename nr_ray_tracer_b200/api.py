@@ -19,7 +19,9 @@ import numpy as np
 from . import _abi as A
 from .scene_config import CameraConfig, SceneGraph, load_scene
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnrrt_b200.so")
+# NRRT_B200_LIB lets a developer point at an experimental build of the SAME library (never at another backend)
+_LIB_PATH = os.environ.get("NRRT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                            "libnrrt_b200.so")
 _lib = None
 
 

@@ -63,9 +63,9 @@ struct Flattener {
     // output arrays
     std::vector<nrrt_node> nodes;
     std::vector<nrrt_box> child_boxes;
-    std::vector<double> sphere_center, sphere_radius;
+    std::vector<double> sphere_rec;  // 4 doubles per sphere
     std::vector<uint32_t> sphere_material, sphere_order, sphere_object;
-    std::vector<double> plane_p, plane_u, plane_v, plane_normal, plane_w, plane_d;
+    std::vector<double> plane_rec;   // 16 doubles per plane
     std::vector<uint32_t> plane_material, plane_order, plane_object;
     std::vector<nrrt_instance> instances;
     std::vector<uint32_t> instance_order;
@@ -232,9 +232,8 @@ struct Flattener {
         const nrrt_object& o = obj(oi);
         switch (o.kind) {
             case NRRT_OBJ_SPHERE: {
-                uint32_t idx = (uint32_t)sphere_radius.size();
-                for (int k = 0; k < 3; ++k) sphere_center.push_back(o.v[k]);
-                sphere_radius.push_back(o.v[3]);
+                uint32_t idx = (uint32_t)sphere_material.size();
+                for (int k = 0; k < 4; ++k) sphere_rec.push_back(o.v[k]);
                 sphere_material.push_back(o.material);
                 sphere_order.push_back(sp.order++);
                 sphere_object.push_back(oi);
@@ -242,14 +241,15 @@ struct Flattener {
             }
             case NRRT_OBJ_QUAD:
             case NRRT_OBJ_TRIANGLE: {
-                uint32_t idx = (uint32_t)plane_d.size();
+                uint32_t idx = (uint32_t)plane_material.size();
                 D3 p{o.v[0], o.v[1], o.v[2]}, u{o.v[3], o.v[4], o.v[5]}, v{o.v[6], o.v[7], o.v[8]};
                 D3 n = u.cross(v);           // plane.rs:109
                 D3 normal = n.normalize();   // :111
                 double d = normal.dot(p);    // :113
                 D3 w = n / n.dot(n);         // :114
-                push3(plane_p, p), push3(plane_u, u), push3(plane_v, v), push3(plane_normal, normal), push3(plane_w, w);
-                plane_d.push_back(d);
+                push3(plane_rec, normal);
+                plane_rec.push_back(d);
+                push3(plane_rec, p), push3(plane_rec, w), push3(plane_rec, u), push3(plane_rec, v);
                 plane_material.push_back(o.material | (o.kind == NRRT_OBJ_TRIANGLE ? NRRT_PLANE_TRIANGLE_BIT : 0u));
                 plane_order.push_back(sp.order++);
                 plane_object.push_back(oi);
@@ -454,19 +454,13 @@ nrrt_host_scene* nrrt_host_build(const nrrt_graph_desc* g) {
         d.child_boxes = f.child_boxes.data();
         d.root = root.ref;
         d.root_box = Flattener::to_box(root.box);
-        d.n_spheres = (uint32_t)f.sphere_radius.size();
-        d.sphere_center = f.sphere_center.data();
-        d.sphere_radius = f.sphere_radius.data();
+        d.n_spheres = (uint32_t)f.sphere_material.size();
+        d.sphere_rec = f.sphere_rec.data();
         d.sphere_material = f.sphere_material.data();
         d.sphere_order = f.sphere_order.data();
         d.sphere_object = f.sphere_object.data();
-        d.n_planes = (uint32_t)f.plane_d.size();
-        d.plane_p = f.plane_p.data();
-        d.plane_u = f.plane_u.data();
-        d.plane_v = f.plane_v.data();
-        d.plane_normal = f.plane_normal.data();
-        d.plane_w = f.plane_w.data();
-        d.plane_d = f.plane_d.data();
+        d.n_planes = (uint32_t)f.plane_material.size();
+        d.plane_rec = f.plane_rec.data();
         d.plane_material = f.plane_material.data();
         d.plane_order = f.plane_order.data();
         d.plane_object = f.plane_object.data();

@@ -31,6 +31,31 @@
 // radiance in f64 in sample order, writes that partial sum to partials[item] and grabs the next item.
 // k_resolve adds a pixel's partials in chunk order: the result does not depend on scheduling, slot count or the
 // number of GPUs (chunk size depends on spp only).
+// Exact unsigned division by a launch-invariant divisor (round-up multiply-shift, branch free):
+// n / d == (t + ((n - t) >> s1)) >> s2 with t = umulhi(m, n).  Replaces three ~20-instruction integer divisions
+// per work-item decode.
+struct FastDiv {
+    uint32_t d, m, s1, s2;
+    __host__ static FastDiv make(uint32_t d) {
+        FastDiv f;
+        f.d = d ? d : 1;
+        uint32_t l = 0;
+        while ((1ull << l) < f.d) ++l;
+        f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - f.d)) / f.d + 1);
+        f.s1 = l < 1 ? l : 1;
+        f.s2 = l > 0 ? l - 1 : 0;
+        return f;
+    }
+    __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
+#ifdef __CUDA_ARCH__
+        uint32_t t = __umulhi(m, n);
+#else
+        uint32_t t = (uint32_t)(((uint64_t)m * n) >> 32);
+#endif
+        return (t + ((n - t) >> s1)) >> s2;
+    }
+};
+
 struct RenderParams {
     uint2 key;               // Philox key
     uint32_t n_owned_pixels; // pixels rendered by this context
@@ -39,15 +64,16 @@ struct RenderParams {
     uint32_t n_items;        // n_owned_pixels * n_chunks
     uint32_t n_slots;        // paths in flight
     uint32_t rank, world, rows_per_block;
+    FastDiv div_pixels, div_width, div_rows;  // by n_owned_pixels, image width, rows_per_block
 };
 
 // owned pixel index -> (x, y): rank owns row-blocks b with b % world == rank
 __device__ __forceinline__ void owned_pixel(const nrrt_camera& cam, const RenderParams& P, uint32_t po, uint32_t& x,
                                             uint32_t& y) {
     uint32_t W = cam.width;
-    uint32_t j = po / W;
+    uint32_t j = P.div_width.div(po);
     x = po - j * W;
-    uint32_t b = j / P.rows_per_block, r = j - b * P.rows_per_block;
+    uint32_t b = P.div_rows.div(j), r = j - b * P.rows_per_block;
     y = (b * P.world + P.rank) * P.rows_per_block + r;
 }
 
@@ -58,7 +84,7 @@ struct WorkItem {
 // item -> pixel + sample range; returns the first sample
 __device__ __forceinline__ uint32_t decode_item(const nrrt_camera& cam, const RenderParams& P, uint32_t item,
                                                 WorkItem& wi) {
-    uint32_t c = item / P.n_owned_pixels, po = item - c * P.n_owned_pixels;
+    uint32_t c = P.div_pixels.div(item), po = item - c * P.n_owned_pixels;
     owned_pixel(cam, P, po, wi.x, wi.y);
     uint32_t first = c * P.chunk;
     wi.sample_end = min(first + P.chunk, cam.samples_per_pixel);
@@ -71,11 +97,13 @@ k_trace_rays(const __grid_constant__ DevScene S, const double* __restrict__ rays
              nrrt_hit* __restrict__ out, unsigned long long* __restrict__ counters) {
     extern __shared__ uint32_t s_stack[];
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    d3 o = ld3(rays + 6 * i), d = ld3(rays + 6 * i + 3);
+    const bool valid = i < n;  // no early return: trace_closest votes across the whole warp
+    d3 o = mk3(0.0, 0.0, 0.0), d = mk3(0.0, 0.0, 0.0);
+    if (valid) o = ld3(rays + 6 * i), d = ld3(rays + 6 * i + 3);
     HitId h;
     TraceCounters tc{0, 0, 0};
-    trace_closest<VISIT_ALL, COUNT>(S, o, d, tmin, tmax, s_stack + threadIdx.x, blockDim.x, h, &tc);
+    trace_closest<VISIT_ALL, COUNT>(S, o, d, tmin, tmax, s_stack + threadIdx.x, NRRT_BLOCK, h, &tc, valid);
+    if (!valid) return;
     nrrt_hit r;
     r.t = h.t;
     r.prim = h.prim;
@@ -111,16 +139,12 @@ k_trace_rays(const __grid_constant__ DevScene S, const double* __restrict__ rays
 
 // One step of Camera::get_ray_color (camera.rs:269-300) in iterative form:  L += T*emitted; T *= color.
 // Returns true while the path is alive.
-__device__ __forceinline__ bool path_step(const DevScene& S, const nrrt_camera& cam, const HitId& h, const Sampler& smp,
-                                          d3& o, d3& d, d3& T, d3& L, uint32_t& bounce) {
-    if (h.prim == NRRT_REF_NONE) {  // camera.rs:298
-        L = add3(L, mul3(T, ld3(cam.background)));
-        return false;
-    }
-    HitRec rec;
-    uint32_t mat = NRRT_REF_TYPE(h.prim) == NRRT_REF_SPHERE ? S.sphere_material[NRRT_REF_INDEX(h.prim)]
-                                                            : (S.plane_material[NRRT_REF_INDEX(h.prim)] & ~NRRT_PLANE_TRIANGLE_BIT);
-    resolve_hit(S, h, o, d, (S.material_flags[mat] & 1u) != 0, rec);
+__device__ __forceinline__ uint32_t hit_material(const DevScene& S, uint32_t prim) {
+    return NRRT_REF_TYPE(prim) == NRRT_REF_SPHERE ? S.sphere_material[NRRT_REF_INDEX(prim)]
+                                                  : (S.plane_material[NRRT_REF_INDEX(prim)] & ~NRRT_PLANE_TRIANGLE_BIT);
+}
+__device__ __forceinline__ bool path_shade(const DevScene& S, const nrrt_camera& cam, const HitRec& rec,
+                                           const Sampler& smp, d3& o, d3& d, d3& T, d3& L, uint32_t& bounce) {
     d3 emitted, atten, nd;
     bool cont = shade_hit(S, rec, d, bounce == 0, smp, bounce + 1, emitted, atten, nd);
     L = add3(L, mul3(T, emitted));
@@ -130,6 +154,16 @@ __device__ __forceinline__ bool path_step(const DevScene& S, const nrrt_camera& 
     d = nd;
     ++bounce;
     return bounce < cam.ray_max_bounces;  // camera.rs:276-278
+}
+__device__ __forceinline__ bool path_step(const DevScene& S, const nrrt_camera& cam, const HitId& h, const Sampler& smp,
+                                          d3& o, d3& d, d3& T, d3& L, uint32_t& bounce) {
+    if (h.prim == NRRT_REF_NONE) {  // camera.rs:298
+        L = add3(L, mul3(T, ld3(cam.background)));
+        return false;
+    }
+    HitRec rec;
+    resolve_hit(S, h, o, d, (S.material_flags[hit_material(S, h.prim)] & 1u) != 0, rec);
+    return path_shade(S, cam, rec, smp, o, d, T, L, bounce);
 }
 
 // Megakernel variant: persistent threads, whole path state in registers.
@@ -143,41 +177,50 @@ k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long segs = 0, paths = 0;
     TraceCounters tc{0, 0, 0};
-    if (w < P.n_slots) {
+    {
         uint32_t item = w;  // the first n_slots items are pre-assigned; the counter starts at n_slots
         WorkItem wi;
+        wi.x = wi.y = wi.sample_end = 0;
         Sampler smp{P.key, 0u, 0u};
         d3 sum = mk3(0.0, 0.0, 0.0);
-        d3 o, d, T, L;
+        d3 o = mk3(0.0, 0.0, 0.0), d = o, T = o, L = o;
         uint32_t bounce = 0;
         bool alive = false, have_item = false;
-        for (;;) {
-            if (!alive) {
+        bool running = w < P.n_slots;
+        while (__any_sync(0xffffffffu, running)) {  // the traversal votes across the warp: keep every lane in the loop
+            if (running && !alive) {
                 if (!have_item) {
-                    if (item >= P.n_items) break;
-                    smp.sample = decode_item(cam, P, item, wi);
-                    smp.pixel = wi.y * cam.width + wi.x;
-                    sum = mk3(0.0, 0.0, 0.0);
-                    have_item = true;
+                    if (item >= P.n_items) {
+                        running = false;
+                    } else {
+                        smp.sample = decode_item(cam, P, item, wi);
+                        smp.pixel = wi.y * cam.width + wi.x;
+                        sum = mk3(0.0, 0.0, 0.0);
+                        have_item = true;
+                    }
                 }
-                camera_ray(cam, wi.x, wi.y, smp, o, d);
-                T = mk3(1.0, 1.0, 1.0);
-                L = mk3(0.0, 0.0, 0.0);
-                bounce = 0;
-                alive = true;
-                ++paths;
+                if (running) {
+                    camera_ray(cam, wi.x, wi.y, smp, o, d);
+                    T = mk3(1.0, 1.0, 1.0);
+                    L = mk3(0.0, 0.0, 0.0);
+                    bounce = 0;
+                    alive = true;
+                    ++paths;
+                }
             }
             HitId h;
-            trace_closest<false, COUNT>(S, o, d, 0.001, NRRT_INF, s_stack + threadIdx.x, blockDim.x, h, &tc);
-            ++segs;
-            alive = path_step(S, cam, h, smp, o, d, T, L, bounce);
-            if (!alive) {
-                sum = add3(sum, L);
-                if (++smp.sample >= wi.sample_end) {  // chunk done: publish its partial sum, fetch the next item
-                    size_t base = (size_t)item * 3;
-                    partials[base] = sum.x, partials[base + 1] = sum.y, partials[base + 2] = sum.z;
-                    item = (uint32_t)atomicAdd(&counters[5], 1ull);
-                    have_item = false;
+            trace_closest<false, COUNT>(S, o, d, 0.001, NRRT_INF, s_stack + threadIdx.x, NRRT_BLOCK, h, &tc, running);
+            if (running) {
+                ++segs;
+                alive = path_step(S, cam, h, smp, o, d, T, L, bounce);
+                if (!alive) {
+                    sum = add3(sum, L);
+                    if (++smp.sample >= wi.sample_end) {  // chunk done: publish its partial sum, fetch the next item
+                        size_t base = (size_t)item * 3;
+                        partials[base] = sum.x, partials[base + 1] = sum.y, partials[base + 2] = sum.z;
+                        item = (uint32_t)atomicAdd(&counters[5], 1ull);
+                        have_item = false;
+                    }
                 }
             }
         }
@@ -238,8 +281,10 @@ struct WfState {
     double* hit_t;     // [n]
     uint32_t* hit_prim;   // [n]
     uint32_t* hit_inst;   // [1 + MAX_DEPTH][n]: depth, inst[0..]
+    double* hit_attr;     // [8][n]: object-space hit point, alpha, beta, object-space direction (MemHitSink)
     uint32_t* queue[2];   // [n] slot indices
     uint32_t* count;      // [2] queue lengths
+    uint32_t* cursor;     // [2] fetch cursors of the persistent extend kernel
     double* partials;     // [n_items][3]
     unsigned long long* counters;  // [0]=segments [1]=paths [5]=next work item
 };
@@ -252,6 +297,8 @@ k_wf_init(const __grid_constant__ nrrt_camera cam, const __grid_constant__ Rende
     if (w == 0) {
         W.count[0] = P.n_slots;
         W.count[1] = 0;
+        W.cursor[0] = 0;
+        W.cursor[1] = 0;
         W.counters[1] += P.n_slots;
     }
     if (w >= P.n_slots) return;
@@ -273,27 +320,54 @@ k_wf_init(const __grid_constant__ nrrt_camera cam, const __grid_constant__ Rende
     W.queue[0][w] = w;
 }
 
-// traverse / intersect: closest hit for every queued ray
-__global__ void __launch_bounds__(NRRT_BLOCK, 4)
+// traverse / intersect: closest hit for every queued ray.
+// Persistent warps with dynamic ray fetch: rays of one warp finish after very different numbers of traversal
+// rounds, so lanes whose ray is done pull the next queued ray (warp-aggregated atomicAdd on a cursor) instead of
+// idling until the slowest lane of the warp finishes.
+#define NRRT_REFILL_MIN 8  // refill once this many lanes of the warp are idle
+__global__ void __launch_bounds__(NRRT_BLOCK, 5)
 k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState W, uint32_t n, uint32_t qin) {
     extern __shared__ uint32_t s_stack[];
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n_in = W.count[qin];
-    if (i == 0) W.count[qin ^ 1] = 0;  // the other queue is filled by the next shade pass
-    if (i >= n_in) return;
-    uint32_t slot = W.queue[qin][i];
-    d3 o = mk3(W.ray[slot], W.ray[(size_t)n + slot], W.ray[2 * (size_t)n + slot]);
-    d3 d = mk3(W.ray[3 * (size_t)n + slot], W.ray[4 * (size_t)n + slot], W.ray[5 * (size_t)n + slot]);
-    HitId h;
-    trace_closest<false, false>(S, o, d, 0.001, NRRT_INF, s_stack + threadIdx.x, blockDim.x, h, nullptr);
-    W.hit_t[slot] = h.t;
-    W.hit_prim[slot] = h.prim;
-    W.hit_inst[slot] = h.depth;
-    for (uint32_t l = 0; l < h.depth; ++l) W.hit_inst[(size_t)(1 + l) * n + slot] = h.inst[l];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_in = W.count[qin];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        W.count[qin ^ 1] = 0;   // the other queue is filled by the next shade pass
+        W.cursor[qin ^ 1] = 0;  // and consumed by the next extend pass
+    }
+    Traversal<false, false> tr;
+    bool has = false, exhausted = false;
+    uint32_t slot = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !has);
+        if (idle && !exhausted && (idle == 0xffffffffu || __popc(idle) >= NRRT_REFILL_MIN)) {
+            const uint32_t want = __popc(idle), leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&W.cursor[qin], want);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + want >= n_in) exhausted = true;
+            if (!has) {
+                uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < n_in) {
+                    slot = W.queue[qin][i];
+                    tr.begin(S, MemCtx{W.ray, W.hit_attr, n, slot}, 0.001, NRRT_INF, nullptr);
+                    has = true;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, has) == 0) break;
+        if (tr.round(S, MemCtx{W.ray, W.hit_attr, n, slot}, 0.001, NRRT_INF, s_stack + threadIdx.x, NRRT_BLOCK, nullptr,
+                     has) && has) {
+            W.hit_t[slot] = tr.best.t;
+            W.hit_prim[slot] = tr.best.prim;
+            W.hit_inst[slot] = tr.best.depth;
+            for (uint32_t l = 0; l < tr.best.depth; ++l) W.hit_inst[(size_t)(1 + l) * n + slot] = tr.best.inst[l];
+            has = false;
+        }
+    }
 }
 
 // shade / scatter, in-slot path regeneration, dynamic work fetch, warp-ballot compaction of the survivors
-__global__ void __launch_bounds__(NRRT_BLOCK)
+__global__ void __launch_bounds__(NRRT_BLOCK, 5)
 k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_camera cam,
            const __grid_constant__ RenderParams P, const __grid_constant__ WfState W, uint32_t qin) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -324,7 +398,23 @@ k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_came
 #pragma unroll
         for (uint32_t l = 0; l < NRRT_MAX_INSTANCE_DEPTH; ++l)
             h.inst[l] = (l < h.depth) ? W.hit_inst[(size_t)(1 + l) * n + slot] : 0u;
+#if !NRRT_HIT_SINK
         survive = path_step(S, cam, h, smp, o, d, T, L, bounce);
+#else
+        if (h.prim == NRRT_REF_NONE) {  // camera.rs:298
+            L = mul3(T, ld3(cam.background));
+            survive = false;
+        } else {
+            HitRec rec;
+            const double* A = W.hit_attr;
+            d3 p_obj = mk3(A[slot], A[(size_t)n + slot], A[2 * (size_t)n + slot]);
+            d3 d_dir = d;
+            if (h.depth) d_dir = mk3(A[5 * (size_t)n + slot], A[6 * (size_t)n + slot], A[7 * (size_t)n + slot]);
+            resolve_hit_attr(S, h, p_obj, A[3 * (size_t)n + slot], A[4 * (size_t)n + slot], d_dir,
+                             (S.material_flags[hit_material(S, h.prim)] & 1u) != 0, rec);
+            survive = path_shade(S, cam, rec, smp, o, d, T, L, bounce);
+        }
+#endif
         if (!survive) {  // path finished: add it to the item's partial sum (sample order)
             sum = add3(mk3(W.sum[slot], W.sum[(size_t)n + slot], W.sum[2 * (size_t)n + slot]), L);
             ++smp.sample;
@@ -403,6 +493,7 @@ struct nrrt_ctx {
     uint32_t* h_count = nullptr;               // pinned, polling ring
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> ev_pool;
+    unsigned persistent_blocks = 592;  // SMs x resident blocks of the extend kernel
 };
 
 #define CK(call)                                                                                   \
@@ -487,6 +578,11 @@ int nrrt_create(int device, nrrt_ctx** out) {
         return NRRT_ERR_CUDA;
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
+            ctx->persistent_blocks = (unsigned)sms * 5u;
+    }
     if ((e = cudaMalloc((void**)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess)
         return bail("cudaMalloc", e);
     if ((e = cudaMallocHost((void**)&ctx->h_count, 64 * sizeof(uint32_t))) != cudaSuccess)
@@ -548,17 +644,11 @@ int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
     UP(child_boxes, sc->child_boxes, (size_t)sc->n_nodes * 2);
     D.root = sc->root;
     D.root_box = sc->root_box;
-    UP(sphere_center, sc->sphere_center, (size_t)sc->n_spheres * 3);
-    UP(sphere_radius, sc->sphere_radius, sc->n_spheres);
+    UP(sphere_rec, sc->sphere_rec, (size_t)sc->n_spheres * 4);
     UP(sphere_material, sc->sphere_material, sc->n_spheres);
     UP(sphere_order, sc->sphere_order, sc->n_spheres);
     UP(sphere_object, sc->sphere_object, sc->n_spheres);
-    UP(plane_p, sc->plane_p, (size_t)sc->n_planes * 3);
-    UP(plane_u, sc->plane_u, (size_t)sc->n_planes * 3);
-    UP(plane_v, sc->plane_v, (size_t)sc->n_planes * 3);
-    UP(plane_normal, sc->plane_normal, (size_t)sc->n_planes * 3);
-    UP(plane_w, sc->plane_w, (size_t)sc->n_planes * 3);
-    UP(plane_d, sc->plane_d, sc->n_planes);
+    UP(plane_rec, sc->plane_rec, (size_t)sc->n_planes * 16);
     UP(plane_material, sc->plane_material, sc->n_planes);
     UP(plane_order, sc->plane_order, sc->n_planes);
     UP(plane_object, sc->plane_object, sc->n_planes);
@@ -780,8 +870,19 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         return NRRT_ERR_LIMIT;
     }
     P.n_items = (uint32_t)n_items64;
-    const uint32_t want_slots = o.max_slots ? o.max_slots : (1u << 20);
+    const uint32_t want_slots = o.max_slots ? o.max_slots : (1u << 21);
     P.n_slots = (uint32_t)std::min<uint64_t>(n_items64, want_slots);
+    P.div_pixels = FastDiv::make(P.n_owned_pixels);
+    P.div_width = FastDiv::make(W);
+    P.div_rows = FastDiv::make(o.rows_per_block);
+    for (uint32_t probe : {0u, 1u, W - 1, W, W + 1, P.n_owned_pixels - 1, P.n_owned_pixels, P.n_items - 1, 0x7fffffffu,
+                           0xfffffff0u}) {  // the multiply-shift must agree with '/' (cheap self-check)
+        if (P.div_pixels.div(probe) != probe / P.div_pixels.d || P.div_width.div(probe) != probe / P.div_width.d ||
+            P.div_rows.div(probe) != probe / P.div_rows.d) {
+            ctx->err = "internal error: FastDiv self-check failed";
+            return NRRT_ERR_INVALID;
+        }
+    }
 
     const bool out_dev = (o.flags & NRRT_RENDER_OUT_DEVICE) != 0;
     const bool counting = (o.flags & NRRT_RENDER_COUNT) != 0;
@@ -797,7 +898,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     };
     size_t o_fb = out_dev ? 0 : carve(fb_bytes);
     size_t o_part = carve((size_t)P.n_items * 3 * sizeof(double));
-    size_t o_ray = 0, o_T = 0, o_sum = 0, o_item = 0, o_sample = 0, o_bounce = 0, o_ht = 0, o_hp = 0, o_hi = 0,
+    size_t o_ray = 0, o_T = 0, o_sum = 0, o_attr = 0, o_item = 0, o_sample = 0, o_bounce = 0, o_ht = 0, o_hp = 0, o_hi = 0,
            o_q0 = 0, o_q1 = 0, o_cnt = 0;
     if (wavefront) {
         o_ray = carve(n * 6 * sizeof(double));
@@ -809,9 +910,10 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         o_ht = carve(n * sizeof(double));
         o_hp = carve(n * sizeof(uint32_t));
         o_hi = carve(n * (1 + NRRT_MAX_INSTANCE_DEPTH) * sizeof(uint32_t));
+        o_attr = carve(n * 8 * sizeof(double));
         o_q0 = carve(n * sizeof(uint32_t));
         o_q1 = carve(n * sizeof(uint32_t));
-        o_cnt = carve(2 * sizeof(uint32_t));
+        o_cnt = carve(4 * sizeof(uint32_t));
     }
     int rc = ensure_scratch(ctx, std::max<size_t>(off, 256));
     if (rc != NRRT_OK) return rc;
@@ -848,9 +950,11 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         Wf.hit_t = (double*)(base + o_ht);
         Wf.hit_prim = (uint32_t*)(base + o_hp);
         Wf.hit_inst = (uint32_t*)(base + o_hi);
+        Wf.hit_attr = (double*)(base + o_attr);
         Wf.queue[0] = (uint32_t*)(base + o_q0);
         Wf.queue[1] = (uint32_t*)(base + o_q1);
         Wf.count = (uint32_t*)(base + o_cnt);
+        Wf.cursor = Wf.count + 2;
         Wf.partials = d_part;
         Wf.counters = ctx->d_counters;
         k_wf_init<<<work_blocks, NRRT_BLOCK, 0, ctx->stream>>>(c, P, Wf);
@@ -880,7 +984,8 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
                 ta = ctx->ev_pool[RING + 2 * timing.size()], tb = ctx->ev_pool[RING + 2 * timing.size() + 1];
                 CK(cudaEventRecord(ta, ctx->stream));
             }
-            k_wf_extend<<<work_blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, Wf, (uint32_t)n, qin);
+            k_wf_extend<<<std::min<unsigned>(work_blocks, ctx->persistent_blocks), NRRT_BLOCK, smem, ctx->stream>>>(
+                ctx->dev, Wf, (uint32_t)n, qin);
             if (timed) {
                 CK(cudaEventRecord(tb, ctx->stream));
                 timing.emplace_back(ta, tb);

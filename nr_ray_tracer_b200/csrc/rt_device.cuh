@@ -16,6 +16,12 @@
 
 #include "../../include/nrrt.h"
 
+#ifndef NRRT_LEAF_VOTE
+#define NRRT_LEAF_VOTE 1   // 1: a warp serves one leaf kind per round (primitive tests OR instance entries)
+#endif
+#ifndef NRRT_HIT_SINK
+#define NRRT_HIT_SINK 1    // 1: the wavefront traverse kernel hands hit attributes to the shade kernel
+#endif
 #define NRRT_STACK_CAP 32          // traversal stack entries per thread (host validates max_stack)
 #define NRRT_REF_POP 0xC0000000u   // type 6: "leave instance level" marker on the stack
 #define NRRT_INF __longlong_as_double(0x7ff0000000000000LL)
@@ -26,17 +32,11 @@ struct DevScene {
     const nrrt_box* child_boxes;
     uint32_t root;
     nrrt_box root_box;
-    const double* sphere_center;
-    const double* sphere_radius;
+    const double* sphere_rec;  // [n][4]: center xyz, radius
     const uint32_t* sphere_material;
     const uint32_t* sphere_order;
     const uint32_t* sphere_object;
-    const double* plane_p;
-    const double* plane_u;
-    const double* plane_v;
-    const double* plane_normal;
-    const double* plane_w;
-    const double* plane_d;
+    const double* plane_rec;   // [n][16]: normal xyz, d, p xyz, w xyz, u xyz, v xyz (one 128-byte line)
     const uint32_t* plane_material;
     const uint32_t* plane_order;
     const uint32_t* plane_object;
@@ -121,10 +121,13 @@ __device__ __forceinline__ void xform_ray(const nrrt_xform* x, d3& o, d3& d) {
         d = mat4_vector(x->to_obj, d);
     }
 }
-__device__ __noinline__ void instance_ray(const DevScene& S, uint32_t inst, d3& o, d3& d) {
+__device__ __forceinline__ void instance_ray_inl(const DevScene& S, uint32_t inst, d3& o, d3& d) {
     const nrrt_instance* in = &S.instances[inst];
     uint32_t f = in->first_xform, n = in->n_xforms;
     for (uint32_t k = 0; k < n; ++k) xform_ray(&S.xforms[f + k], o, d);
+}
+__device__ __noinline__ void instance_ray(const DevScene& S, uint32_t inst, d3& o, d3& d) {
+    instance_ray_inl(S, inst, o, d);
 }
 // Hit back to the parent space (translate.rs:45-48, rotate.rs:100-105, scale.rs:82-85: point only).
 __device__ __noinline__ void instance_hit_back(const DevScene& S, uint32_t inst, d3& point, d3& normal) {
@@ -168,8 +171,10 @@ __device__ __noinline__ bool box_hit_exact(const nrrt_box* b, d3 o, d3 d, double
 // --------------------------------------------------------------------------- primitives
 // Sphere::hit (objects/sphere.rs:105-147): returns t or NaN for a miss.
 __device__ __forceinline__ double sphere_t(const DevScene& S, uint32_t i, d3 o, d3 d, double tmin, double tmax) {
-    d3 c = ld3(S.sphere_center + 3 * (size_t)i);
-    double r = S.sphere_radius[i];
+    const double2* rec = reinterpret_cast<const double2*>(S.sphere_rec) + 2 * (size_t)i;
+    double2 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+    d3 c = mk3(r0.x, r0.y, r1.x);
+    double r = r1.y;
     d3 ec = sub3(c, o);
     double a = dot3(d, d);
     double h = dot3(ec, d);
@@ -184,19 +189,27 @@ __device__ __forceinline__ double sphere_t(const DevScene& S, uint32_t i, d3 o, 
     return __longlong_as_double(0x7ff8000000000000LL);
 }
 
-// Plane::hit (objects/plane.rs:141-174): returns t or NaN; alpha/beta through pointers.
+// Plane::hit (objects/plane.rs:141-174): returns t or NaN; alpha/beta and the hit point through pointers.
+// `tbest` = t of the best hit so far: a candidate with t > tbest can never win (equal t still can, by leaf
+// order), so its interior test is skipped — same result as the reference, fewer flops.
 __device__ __forceinline__ double plane_t(const DevScene& S, uint32_t i, d3 o, d3 d, double tmin, double tmax,
-                                          double* alpha_out, double* beta_out) {
+                                          double tbest, double* alpha_out, double* beta_out, d3* point_out) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    d3 n = ld3(S.plane_normal + 3 * (size_t)i);
+    const double2* rec = reinterpret_cast<const double2*>(S.plane_rec) + 8 * (size_t)i;
+    double2 q0 = __ldg(rec), q1 = __ldg(rec + 1);  // normal xyz, d
+    d3 n = mk3(q0.x, q0.y, q1.x);
     double denom = dot3(n, d);
     if (fabs(denom) < 1e-8) return nan;
-    double t = xdiv(xsub(S.plane_d[i], dot3(n, o)), denom);
+    double t = xdiv(xsub(q1.y, dot3(n, o)), denom);
     if (!(tmin <= t && t <= tmax)) return nan;  // Interval::contains
-    d3 q = sub3(ray_at(o, d, t), ld3(S.plane_p + 3 * (size_t)i));
-    d3 w = ld3(S.plane_w + 3 * (size_t)i);
-    double alpha = dot3(w, cross3(q, ld3(S.plane_v + 3 * (size_t)i)));
-    double beta = dot3(w, cross3(ld3(S.plane_u + 3 * (size_t)i), q));
+    if (t > tbest) return nan;
+    double2 q2 = __ldg(rec + 2), q3 = __ldg(rec + 3), q4 = __ldg(rec + 4), q5 = __ldg(rec + 5), q6 = __ldg(rec + 6),
+            q7 = __ldg(rec + 7);
+    d3 pp = mk3(q2.x, q2.y, q3.x), w = mk3(q3.y, q4.x, q4.y), uu = mk3(q5.x, q5.y, q6.x), vv = mk3(q6.y, q7.x, q7.y);
+    d3 point = ray_at(o, d, t);
+    d3 q = sub3(point, pp);
+    double alpha = dot3(w, cross3(q, vv));
+    double beta = dot3(w, cross3(uu, q));
     bool interior;
     if (S.plane_material[i] & NRRT_PLANE_TRIANGLE_BIT)
         interior = alpha > 0.0 && beta > 0.0 && xadd(alpha, beta) < 1.0;
@@ -205,6 +218,7 @@ __device__ __forceinline__ double plane_t(const DevScene& S, uint32_t i, d3 o, d
     if (!interior) return nan;
     *alpha_out = alpha;
     *beta_out = beta;
+    *point_out = point;
     return t;
 }
 
@@ -291,44 +305,90 @@ __device__ __forceinline__ bool root_box_test(const nrrt_box* b, const Ray32& r3
     return box_hit_exact(b, o, d, tmin, tmax);
 }
 
-// BVH::hit (objects/object.rs:89-121) over the flattened scene.
+// Per-query context handed to begin()/round() on every call instead of being stored in the traversal state, so
+// base pointers are re-read from the kernel's constant bank rather than pinned in registers.
+//   get(): the world-space ray (needed again when an instance is left)
+//   put(): attributes of a candidate that just became the best hit
+// Fixed-ray queries / megakernel: ray in registers, attributes recomputed later by resolve_hit.
+struct RegCtx {
+    d3 o, d;
+    __device__ __forceinline__ void get(d3& oo, d3& dd) const { oo = o, dd = d; }
+    __device__ __forceinline__ void put(uint32_t, d3, double, double, d3) const {}
+};
+// Wavefront: ray re-read from the SoA path state (saves 12 registers across the node loop); attributes go straight
+// into the slot's hit record so the shade kernel neither re-applies the wrapper chain to the ray nor recomputes
+// alpha/beta.  attr = [8][n]: object-space hit point xyz, alpha, beta, and (hits inside an instance only) the
+// object-space ray direction xyz that decides front_face.
+struct MemCtx {
+    const double* ray;  // [6][n]
+    double* attr;       // [8][n]
+    uint32_t n, slot;
+    __device__ __forceinline__ void get(d3& oo, d3& dd) const {
+        oo = mk3(ray[slot], ray[(size_t)n + slot], ray[2 * (size_t)n + slot]);
+        dd = mk3(ray[3 * (size_t)n + slot], ray[4 * (size_t)n + slot], ray[5 * (size_t)n + slot]);
+    }
+    __device__ __forceinline__ void put(uint32_t level, d3 p, double a, double b, d3 dobj) const {
+#if NRRT_HIT_SINK
+        attr[slot] = p.x, attr[(size_t)n + slot] = p.y, attr[2 * (size_t)n + slot] = p.z;
+        attr[3 * (size_t)n + slot] = a, attr[4 * (size_t)n + slot] = b;
+        if (level) attr[5 * (size_t)n + slot] = dobj.x, attr[6 * (size_t)n + slot] = dobj.y, attr[7 * (size_t)n + slot] = dobj.z;
+#endif
+    }
+};
+
+// BVH::hit (objects/object.rs:89-121) over the flattened scene, as a resumable state machine.
 //   VISIT_ALL = true : visits exactly the reference's node set (no pruning by the best hit so far)
 //   VISIT_ALL = false: near-first order + conservative pruning by the best t (same result, fewer visits)
-// `stack` is this thread's slice of shared memory, stride `sstride` (bank-conflict free).
 //
-// Loop shape ("while-while"): the inner loop walks inner nodes only — cheap f32 work every lane of the warp can do
-// in lock step — until the lane holds a leaf; leaves (exact f64 primitive tests, instance entry/exit) are then
-// processed together, so the expensive divergent part runs once per round instead of once per node step.
+// begin() starts a query; round() advances it by one "round": the inner loop walks inner nodes only — cheap f32
+// work every lane of a warp does in lock step — until the lane holds a leaf; then the warp VOTES which kind of
+// leaf to process this round (exact f64 primitive tests, or instance entries) and only the lanes holding that
+// kind advance, the others keep their leaf for a later round.  The two expensive, mutually divergent code paths
+// therefore never serialise inside one round, and each runs with as many lanes as possible.
+// round() must be called by ALL 32 lanes of the warp (lanes without a query pass has = false); it returns true
+// when the lane's query is finished.  Keeping the state resumable lets a persistent warp swap finished rays for
+// fresh ones between rounds.
 template <bool VISIT_ALL, bool COUNT>
-__device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, double tmin, double tmax,
-                                              uint32_t* stack, uint32_t sstride, HitId& best, TraceCounters* cnt) {
-    best.t = NRRT_INF;
-    best.prim = NRRT_REF_NONE;
-    best.depth = 0;
-#pragma unroll
-    for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) best.inst[k] = 0;
-
+struct Traversal {
+    d3 o, d;         // ray in the current space (world, or the object space of the innermost entered instance)
+    Ray32 r32;
+    float tcull;
+    uint32_t sp, cur, level;
     uint32_t cur_inst[NRRT_MAX_INSTANCE_DEPTH];
+    HitId best;
+
+    // filter bounds of the query range; the margins cover the rounding
+    static __device__ __forceinline__ float lo32(double tmin) { return (float)tmin; }
+    static __device__ __forceinline__ float hi32(double tmax) { return (tmax < 3.0e38) ? (float)tmax : 3.4e38f; }
+
+    template <class Ctx>
+    __device__ __forceinline__ void begin(const DevScene& S, const Ctx& ctx, double tmin, double tmax,
+                                          TraceCounters* cnt) {
+        const float tmin32 = lo32(tmin), tmax32 = hi32(tmax);
+        best.t = NRRT_INF;
+        best.prim = NRRT_REF_NONE;
+        best.depth = 0;
 #pragma unroll
-    for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) cur_inst[k] = 0;
-    uint32_t level = 0;
-    d3 o = wo, d = wd;
-    const Ray32 w32 = make_ray32(wo, wd);
-    Ray32 r32 = w32;
-    const float tmin32 = (float)tmin;                              // filter bounds; margins cover the rounding
-    const float tmax32 = (tmax < 3.0e38) ? (float)tmax : 3.4e38f;
-    float tcull = 3.4e38f;                                         // f32 upper bound of best.t (+ slack)
+        for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) best.inst[k] = 0, cur_inst[k] = 0;
+        level = 0;
+        ctx.get(o, d);
+        r32 = make_ray32(o, d);
+        tcull = 3.4e38f;                                    // f32 upper bound of best.t (+ slack)
+        sp = 0;
+        cur = S.root;
+        // root of the scene: an inner node tests its own box (object.rs:102)
+        if (NRRT_REF_TYPE(cur) == NRRT_REF_NODE &&
+            !root_box_test<COUNT>(&S.root_box, r32, o, d, tmin, tmax, tmin32, tmax32, cnt))
+            cur = NRRT_REF_NONE;
+    }
 
-    uint32_t sp = 0;
-    uint32_t cur = S.root;
-    // root of the scene: an inner node tests its own box (object.rs:102)
-    if (NRRT_REF_TYPE(cur) == NRRT_REF_NODE &&
-        !root_box_test<COUNT>(&S.root_box, r32, o, d, tmin, tmax, tmin32, tmax32, cnt))
-        cur = NRRT_REF_NONE;
-
-    for (;;) {
+    // `stack` is this thread's slice of shared memory, stride `sstride` (bank-conflict free).
+    template <class Ctx>
+    __device__ __forceinline__ bool round(const DevScene& S, const Ctx& ctx, double tmin, double tmax, uint32_t* stack,
+                                          uint32_t sstride, TraceCounters* cnt, bool has) {
+        const float tmin32 = lo32(tmin), tmax32 = hi32(tmax);
         // ---------------- phase 1: inner nodes
-        while (NRRT_REF_TYPE(cur) == NRRT_REF_NODE) {
+        while (has && NRRT_REF_TYPE(cur) == NRRT_REF_NODE) {
             uint32_t ni = NRRT_REF_INDEX(cur);
             const float4* np = S.nodes + 4 * (size_t)ni;
             float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
@@ -374,13 +434,29 @@ __device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, d
                 }
             }
         }
-        // ---------------- phase 2: one leaf (primitive / instance / level marker), or nothing left
-        const uint32_t ty = NRRT_REF_TYPE(cur);
-        if (ty == NRRT_REF_SPHERE || ty == NRRT_REF_PLANE) {
+        // ---------------- phase 2: the warp votes for one kind of leaf
+        const uint32_t ty = has ? NRRT_REF_TYPE(cur) : (uint32_t)NRRT_REF_EMPTY;
+        const bool is_prim = (ty == NRRT_REF_SPHERE || ty == NRRT_REF_PLANE), is_inst = (ty == NRRT_REF_INSTANCE);
+        const unsigned m_prim = __ballot_sync(0xffffffffu, is_prim), m_inst = __ballot_sync(0xffffffffu, is_inst);
+        if (!has) return true;
+#if NRRT_LEAF_VOTE
+        const bool serve_inst = __popc(m_inst) > __popc(m_prim);
+#else
+        const bool serve_inst = is_inst;  // no vote: every lane processes whatever leaf it holds
+        (void)m_prim, (void)m_inst;
+#endif
+        if (is_prim) {
+            if (serve_inst) return false;  // wait: this round enters instances
             if (COUNT) cnt->prims++;
-            double a_, b_;
-            double t = (ty == NRRT_REF_SPHERE) ? sphere_t(S, NRRT_REF_INDEX(cur), o, d, tmin, tmax)
-                                               : plane_t(S, NRRT_REF_INDEX(cur), o, d, tmin, tmax, &a_, &b_);
+            double a_ = 0.0, b_ = 0.0;
+            d3 pt;
+            double t;
+            if (ty == NRRT_REF_SPHERE) {
+                t = sphere_t(S, NRRT_REF_INDEX(cur), o, d, tmin, tmax);
+                pt = ray_at(o, d, t);
+            } else {
+                t = plane_t(S, NRRT_REF_INDEX(cur), o, d, tmin, tmax, VISIT_ALL ? NRRT_INF : best.t, &a_, &b_, &pt);
+            }
             if (t == t) {
                 bool take = t < best.t;
                 if (!take && t == best.t) take = tie_candidate_wins(S, cur, cur_inst, level, best);
@@ -390,19 +466,21 @@ __device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, d
                     best.depth = level;
 #pragma unroll
                     for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) best.inst[k] = cur_inst[k];
+                    ctx.put(level, pt, a_, b_, d);
                     // f32 upper bound of t with slack far above any f64 rounding discrepancy
                     float tf = (float)t;
                     tcull = tf + fabsf(tf) * 1.0e-6f + 1e-30f;
                 }
             }
-        } else if (ty == NRRT_REF_INSTANCE) {
+        } else if (is_inst) {
+            if (!serve_inst) return false;  // wait: this round tests primitives
             // enter an instance: transform the ray (exactly, wrapper by wrapper), test the nested root's box
             uint32_t ii = NRRT_REF_INDEX(cur);
             const nrrt_instance* in = &S.instances[ii];
             uint32_t inner = in->inner;
             if (inner != NRRT_REF_NONE && level < NRRT_MAX_INSTANCE_DEPTH) {
                 d3 no = o, nd = d;
-                instance_ray(S, ii, no, nd);
+                instance_ray_inl(S, ii, no, nd);
                 Ray32 n32 = make_ray32(no, nd);
                 bool enter = true;
                 if (NRRT_REF_TYPE(inner) == NRRT_REF_NODE)
@@ -415,25 +493,46 @@ __device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, d
                     o = no, d = nd;
                     r32 = n32;
                     cur = inner;
-                    continue;
+                    return false;
                 }
             }
-        } else if (cur == NRRT_REF_POP) {
-            // leave the instance: rebuild the parent-level ray from the world ray (bit-identical recomputation)
-            --level;
-            o = wo, d = wd;
-            if (level == 0) {
-                r32 = w32;
-            } else {
-                for (uint32_t l = 0; l < level; ++l) instance_ray(S, cur_inst[l], o, d);
-                r32 = make_ray32(o, d);
-            }
         }
-        // next
-        if (sp == 0) break;
-        --sp;
-        cur = stack[sp * sstride];
+        // next pending entry; level markers are consumed on the way (leaving an instance rebuilds the parent-level
+        // ray from the world ray: a bit-identical recomputation).  Phase 1 may already have popped a marker.
+        bool in_hand = (cur == NRRT_REF_POP);
+        for (;;) {
+            if (!in_hand) {
+                if (sp == 0) {
+                    cur = NRRT_REF_NONE;
+                    return true;
+                }
+                --sp;
+                cur = stack[sp * sstride];
+            }
+            in_hand = false;
+            if (cur != NRRT_REF_POP) return false;
+            --level;
+            ctx.get(o, d);
+            for (uint32_t l = 0; l < level; ++l) instance_ray(S, cur_inst[l], o, d);
+            r32 = make_ray32(o, d);
+        }
     }
+};
+
+// Convenience: run one query per lane to completion (fixed-ray queries, megakernel).  Must be called by all 32
+// lanes of the warp; lanes with active = false only take part in the votes.
+template <bool VISIT_ALL, bool COUNT>
+__device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, double tmin, double tmax,
+                                              uint32_t* stack, uint32_t sstride, HitId& best, TraceCounters* cnt,
+                                              bool active) {
+    Traversal<VISIT_ALL, COUNT> tr;
+    const RegCtx ctx{wo, wd};
+    if (active) tr.begin(S, ctx, tmin, tmax, cnt);
+    bool running = active;
+    while (__any_sync(0xffffffffu, running)) {
+        if (tr.round(S, ctx, tmin, tmax, stack, sstride, cnt, running)) running = false;
+    }
+    best = tr.best;
 }
 
 // --------------------------------------------------------------------------- hit record
@@ -454,7 +553,7 @@ __device__ __forceinline__ void resolve_hit(const DevScene& S, const HitId& h, d
     d3 point = ray_at(o, d, h.t), outward;
     double u = 0.0, v = 0.0;
     if (ty == NRRT_REF_SPHERE) {
-        d3 c = ld3(S.sphere_center + 3 * (size_t)ix);
+        d3 c = ld3(S.sphere_rec + 4 * (size_t)ix);
         outward = normalize3(sub3(point, c));  // sphere.rs:151
         if (want_uv) {                         // sphere.rs:153-159
             const double PI = 3.14159265358979323846264338327950288;
@@ -465,14 +564,49 @@ __device__ __forceinline__ void resolve_hit(const DevScene& S, const HitId& h, d
         }
         rec.material = S.sphere_material[ix];
     } else {
-        outward = ld3(S.plane_normal + 3 * (size_t)ix);
-        d3 q = sub3(point, ld3(S.plane_p + 3 * (size_t)ix));
-        d3 w = ld3(S.plane_w + 3 * (size_t)ix);
-        u = dot3(w, cross3(q, ld3(S.plane_v + 3 * (size_t)ix)));  // alpha
-        v = dot3(w, cross3(ld3(S.plane_u + 3 * (size_t)ix), q));  // beta
+        const double* pr = S.plane_rec + 16 * (size_t)ix;
+        outward = ld3(pr);
+        d3 q = sub3(point, ld3(pr + 4));
+        d3 w = ld3(pr + 7);
+        u = dot3(w, cross3(q, ld3(pr + 13)));  // alpha
+        v = dot3(w, cross3(ld3(pr + 10), q));  // beta
         rec.material = S.plane_material[ix] & ~NRRT_PLANE_TRIANGLE_BIT;
     }
     double sign = signum(dot3(d, outward));
+    rec.front_face = sign < 0.0;
+    d3 normal = scale3(outward, -sign);
+    for (uint32_t l = h.depth; l-- > 0;) instance_hit_back(S, h.inst[l], point, normal);
+    rec.point = point;
+    rec.normal = normal;
+    rec.u = u;
+    rec.v = v;
+}
+
+// Same HitRecord, from the attributes the wavefront traverse kernel stored when the candidate won (MemHitSink):
+// p_obj / alpha / beta are the very values the primitive test computed, d_dir is the ray direction in the
+// primitive's space (the world direction for depth 0).
+__device__ __forceinline__ void resolve_hit_attr(const DevScene& S, const HitId& h, d3 p_obj, double alpha, double beta,
+                                                 d3 d_dir, bool want_uv, HitRec& rec) {
+    uint32_t ty = NRRT_REF_TYPE(h.prim), ix = NRRT_REF_INDEX(h.prim);
+    d3 point = p_obj, outward;
+    double u = alpha, v = beta;
+    if (ty == NRRT_REF_SPHERE) {
+        d3 c = ld3(S.sphere_rec + 4 * (size_t)ix);
+        outward = normalize3(sub3(point, c));  // sphere.rs:151
+        u = 0.0, v = 0.0;
+        if (want_uv) {                         // sphere.rs:153-159
+            const double PI = 3.14159265358979323846264338327950288;
+            double theta = acos(-outward.y);
+            double phi = xadd(atan2(-outward.z, outward.x), PI);
+            u = xdiv(phi, xmul(2.0, PI));
+            v = xdiv(theta, PI);
+        }
+        rec.material = S.sphere_material[ix];
+    } else {
+        outward = ld3(S.plane_rec + 16 * (size_t)ix);
+        rec.material = S.plane_material[ix] & ~NRRT_PLANE_TRIANGLE_BIT;
+    }
+    double sign = signum(dot3(d_dir, outward));
     rec.front_face = sign < 0.0;
     d3 normal = scale3(outward, -sign);
     for (uint32_t l = h.depth; l-- > 0;) instance_hit_back(S, h.inst[l], point, normal);
@@ -649,8 +783,12 @@ __device__ __forceinline__ bool shade_hit(const DevScene& S, const HitRec& h, d3
     const nrrt_material* m = &S.materials[h.material];
     uint32_t kind = m->kind;
     emitted = mk3(0.0, 0.0, 0.0);
+    // Lambertian and Metal both draw random_in_unit_sphere as their only random input (lambertian.rs:46,
+    // metal.rs:80-81) with the same counter, so the divergent rejection loop runs once for both kinds.
+    d3 rnd = mk3(0.0, 0.0, 0.0);
+    if (kind == NRRT_MAT_LAMBERTIAN || kind == NRRT_MAT_METAL) rnd = random_in_unit_sphere(smp, stage);
     if (kind == NRRT_MAT_LAMBERTIAN) {  // lambertian.rs:39-55
-        d3 dir = add3(h.normal, random_in_unit_sphere(smp, stage));
+        d3 dir = add3(h.normal, rnd);
         if (fabs(dir.x) < 1e-8 && fabs(dir.y) < 1e-8 && fabs(dir.z) < 1e-8) dir = h.normal;
         new_dir = dir;
         atten = texture_color(S, m->texture, h.u, h.v, h.point);
@@ -658,7 +796,7 @@ __device__ __forceinline__ bool shade_hit(const DevScene& S, const HitRec& h, d3
     }
     if (kind == NRRT_MAT_METAL) {  // metal.rs:73-91
         d3 refl = sub3(rd, scale3(h.normal, xmul(2.0, dot3(rd, h.normal))));  // glam reflect
-        d3 dir = add3(normalize3(refl), scale3(random_in_unit_sphere(smp, stage), m->param));
+        d3 dir = add3(normalize3(refl), scale3(rnd, m->param));
         if (dot3(dir, h.normal) > 0.0) {
             new_dir = dir;
             atten = texture_color(S, m->texture, h.u, h.v, h.point);

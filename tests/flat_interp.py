@@ -33,17 +33,14 @@ class FlatScene:
         self.root = d.root
         self.root_box = (list(d.root_box.lo), list(d.root_box.hi))
         ns, npl = d.n_spheres, d.n_planes
-        self.sc = _arr(d.sphere_center, ns * 3, np.float64).reshape(-1, 3)
-        self.sr = _arr(d.sphere_radius, ns, np.float64)
+        srec = _arr(d.sphere_rec, ns * 4, np.float64).reshape(-1, 4)
+        self.sc, self.sr = srec[:, :3].copy(), srec[:, 3].copy()
         self.sm = _arr(d.sphere_material, ns, np.uint32)
         self.so = _arr(d.sphere_order, ns, np.uint32)
         self.sobj = _arr(d.sphere_object, ns, np.uint32)
-        self.pp = _arr(d.plane_p, npl * 3, np.float64).reshape(-1, 3)
-        self.pu = _arr(d.plane_u, npl * 3, np.float64).reshape(-1, 3)
-        self.pv = _arr(d.plane_v, npl * 3, np.float64).reshape(-1, 3)
-        self.pn = _arr(d.plane_normal, npl * 3, np.float64).reshape(-1, 3)
-        self.pw = _arr(d.plane_w, npl * 3, np.float64).reshape(-1, 3)
-        self.pd = _arr(d.plane_d, npl, np.float64)
+        prec = _arr(d.plane_rec, npl * 16, np.float64).reshape(-1, 16)  # normal, d, p, w, u, v
+        self.pn, self.pd, self.pp = prec[:, 0:3].copy(), prec[:, 3].copy(), prec[:, 4:7].copy()
+        self.pw, self.pu, self.pv = prec[:, 7:10].copy(), prec[:, 10:13].copy(), prec[:, 13:16].copy()
         self.pm = _arr(d.plane_material, npl, np.uint32)
         self.po = _arr(d.plane_order, npl, np.uint32)
         self.pobj = _arr(d.plane_object, npl, np.uint32)

@@ -104,8 +104,18 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
+def host_threads() -> int:
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the reference arm ignores that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def oracle_sample(spp_sample: int, n_threads: int = 0, repeats: int = 1):
     """Times the oracle on the bench workload at reduced spp.  Returns (Mrays/s, seconds, segments, threads)."""
+    if n_threads <= 0:
+        n_threads = host_threads()
     from nr_ray_tracer_b200.scene_config import CameraConfig, load_scene
     from oracle import oracle as O
     g = load_scene(SCENE, camera_override=CameraConfig(width=WIDTH, height=HEIGHT, samples_per_pixel=spp_sample,
@@ -119,7 +129,7 @@ def oracle_sample(spp_sample: int, n_threads: int = 0, repeats: int = 1):
         dt = time.perf_counter() - t0
         if best is None or dt < best[1]:
             best = (cnt["segments"] / dt / 1e6, dt, cnt["segments"])
-    return best + (O.num_threads() if n_threads <= 0 else n_threads,)
+    return best + (n_threads,)
 
 
 def run_reference(args):
@@ -349,8 +359,8 @@ def main():
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--spp", type=int, default=SPP)
-    ap.add_argument("--cpu-spp", type=int, default=16, help="spp of the bounded cpu_baseline sample")
-    ap.add_argument("--ref-spp", type=int, default=8, help="spp per step of the --impl reference arm")
+    ap.add_argument("--cpu-spp", type=int, default=128, help="spp of the bounded cpu_baseline sample")
+    ap.add_argument("--ref-spp", type=int, default=32, help="spp per step of the --impl reference arm")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -345,6 +345,8 @@ typedef struct nrrt_render_stats {
     uint64_t node_visits;  /* NRRT_RENDER_COUNT only: inner nodes fetched      */
     uint64_t box_exact;    /*   f32-inconclusive / root box tests done in f64  */
     uint64_t prim_tests;   /*   exact primitive tests                          */
+    uint64_t inst_entries; /*   wrapper chains applied to a ray (instance leaves reached) */
+    uint64_t inst_misses;  /*   ... of which the nested root box was missed    */
 } nrrt_render_stats;
 
 typedef void (*nrrt_progress_fn)(uint64_t pixels_done, uint64_t pixels_total, void* user);

@@ -121,7 +121,8 @@ class RenderOpts(C.Structure):
 class RenderStats(C.Structure):
     _fields_ = [("paths", u64), ("segments", u64), ("launches", u64), ("device_ms", f64), ("extend_ms", f64),
                 ("extend_launches", u64), ("pixels", u32), ("_pad", u32),
-                ("node_visits", u64), ("box_exact", u64), ("prim_tests", u64)]
+                ("node_visits", u64), ("box_exact", u64), ("prim_tests", u64), ("inst_entries", u64),
+                ("inst_misses", u64)]
 
 
 PROGRESS_FN = C.CFUNCTYPE(None, u64, u64, C.c_void_p)

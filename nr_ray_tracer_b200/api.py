@@ -186,7 +186,7 @@ class Context:
                                       None, C.byref(st)))
         stats = {k: getattr(st, k) for k in ("paths", "segments", "launches", "device_ms", "extend_ms",
                                              "extend_launches", "pixels", "node_visits", "box_exact",
-                                             "prim_tests")}
+                                             "prim_tests", "inst_entries", "inst_misses")}
         return (None if out_device_ptr is not None else out), stats
 
 

@@ -101,7 +101,7 @@ k_trace_rays(const __grid_constant__ DevScene S, const double* __restrict__ rays
     d3 o = mk3(0.0, 0.0, 0.0), d = mk3(0.0, 0.0, 0.0);
     if (valid) o = ld3(rays + 6 * i), d = ld3(rays + 6 * i + 3);
     HitId h;
-    TraceCounters tc{0, 0, 0};
+    TraceCounters tc{0, 0, 0, 0, 0};
     trace_closest<VISIT_ALL, COUNT>(S, o, d, tmin, tmax, s_stack + threadIdx.x, NRRT_BLOCK, h, &tc, valid);
     if (!valid) return;
     nrrt_hit r;
@@ -176,7 +176,7 @@ k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
     extern __shared__ uint32_t s_stack[];
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long segs = 0, paths = 0;
-    TraceCounters tc{0, 0, 0};
+    TraceCounters tc{0, 0, 0, 0, 0};
     {
         uint32_t item = w;  // the first n_slots items are pre-assigned; the counter starts at n_slots
         WorkItem wi;
@@ -246,6 +246,8 @@ k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
         atomicAdd(&counters[2], (unsigned long long)tc.nodes);
         atomicAdd(&counters[3], (unsigned long long)tc.exact);
         atomicAdd(&counters[4], (unsigned long long)tc.prims);
+        atomicAdd(&counters[6], (unsigned long long)tc.inst);
+        atomicAdd(&counters[7], (unsigned long long)tc.inst_miss);
     }
 }
 
@@ -280,7 +282,7 @@ struct WfState {
     uint32_t* bounce;  // [n]
     double* hit_t;     // [n]
     uint32_t* hit_prim;   // [n]
-    uint32_t* hit_inst;   // [1 + MAX_DEPTH][n]: depth, inst[0..]
+    uint32_t* hit_inst;   // [MAX_DEPTH][n]: word 0 = depth | inst[0] << 3, words 1.. = inst[1..] (depth >= 2 only)
     double* hit_attr;     // [8][n]: object-space hit point, alpha, beta, object-space direction (MemHitSink)
     uint32_t* queue[2];   // [n] slot indices
     uint32_t* count;      // [2] queue lengths
@@ -324,7 +326,9 @@ k_wf_init(const __grid_constant__ nrrt_camera cam, const __grid_constant__ Rende
 // Persistent warps with dynamic ray fetch: rays of one warp finish after very different numbers of traversal
 // rounds, so lanes whose ray is done pull the next queued ray (warp-aggregated atomicAdd on a cursor) instead of
 // idling until the slowest lane of the warp finishes.
-#define NRRT_REFILL_MIN 8  // refill once this many lanes of the warp are idle
+#ifndef NRRT_REFILL_MIN
+#define NRRT_REFILL_MIN 16  // refill once this many lanes of the warp are idle (8/16 measured: 16 wins on Cornell + teapot)
+#endif
 __global__ void __launch_bounds__(NRRT_BLOCK, 5)
 k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState W, uint32_t n, uint32_t qin) {
     extern __shared__ uint32_t s_stack[];
@@ -359,15 +363,19 @@ k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState 
                      has) && has) {
             W.hit_t[slot] = tr.best.t;
             W.hit_prim[slot] = tr.best.prim;
-            W.hit_inst[slot] = tr.best.depth;
-            for (uint32_t l = 0; l < tr.best.depth; ++l) W.hit_inst[(size_t)(1 + l) * n + slot] = tr.best.inst[l];
+            W.hit_inst[slot] = tr.best.depth | (tr.best.inst[0] << 3);
+            if (tr.best.depth > 1)
+                for (uint32_t l = 1; l < tr.best.depth; ++l) W.hit_inst[(size_t)l * n + slot] = tr.best.inst[l];
             has = false;
         }
     }
 }
 
 // shade / scatter, in-slot path regeneration, dynamic work fetch, warp-ballot compaction of the survivors
-__global__ void __launch_bounds__(NRRT_BLOCK, 5)
+#ifndef NRRT_SHADE_MINBLOCKS
+#define NRRT_SHADE_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(NRRT_BLOCK, NRRT_SHADE_MINBLOCKS)
 k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_camera cam,
            const __grid_constant__ RenderParams P, const __grid_constant__ WfState W, uint32_t qin) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -394,10 +402,14 @@ k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_came
         HitId h;
         h.t = W.hit_t[slot];
         h.prim = W.hit_prim[slot];
-        h.depth = (h.prim == NRRT_REF_NONE) ? 0u : W.hit_inst[slot];
+        {
+            const uint32_t w0 = (h.prim == NRRT_REF_NONE) ? 0u : W.hit_inst[slot];
+            h.depth = w0 & 7u;
+            h.inst[0] = w0 >> 3;
 #pragma unroll
-        for (uint32_t l = 0; l < NRRT_MAX_INSTANCE_DEPTH; ++l)
-            h.inst[l] = (l < h.depth) ? W.hit_inst[(size_t)(1 + l) * n + slot] : 0u;
+            for (uint32_t l = 1; l < NRRT_MAX_INSTANCE_DEPTH; ++l)
+                h.inst[l] = (l < h.depth) ? W.hit_inst[(size_t)l * n + slot] : 0u;
+        }
 #if !NRRT_HIT_SINK
         survive = path_step(S, cam, h, smp, o, d, T, L, bounce);
 #else
@@ -909,7 +921,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         o_bounce = carve(n * sizeof(uint32_t));
         o_ht = carve(n * sizeof(double));
         o_hp = carve(n * sizeof(uint32_t));
-        o_hi = carve(n * (1 + NRRT_MAX_INSTANCE_DEPTH) * sizeof(uint32_t));
+        o_hi = carve(n * NRRT_MAX_INSTANCE_DEPTH * sizeof(uint32_t));
         o_attr = carve(n * 8 * sizeof(double));
         o_q0 = carve(n * sizeof(uint32_t));
         o_q1 = carve(n * sizeof(uint32_t));
@@ -1050,7 +1062,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
             if (o.world == 1) break;
         }
     }
-    unsigned long long hc[5] = {0, 0, 0, 0, 0};
+    unsigned long long hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (progress) progress(P.n_owned_pixels, P.n_owned_pixels, user);
@@ -1068,6 +1080,8 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         stats->node_visits = hc[2];
         stats->box_exact = hc[3];
         stats->prim_tests = hc[4];
+        stats->inst_entries = hc[6];
+        stats->inst_misses = hc[7];
     }
     return NRRT_OK;
 }

@@ -231,7 +231,7 @@ struct HitId {
 };
 
 struct TraceCounters {
-    uint32_t nodes, exact, prims;
+    uint32_t nodes, exact, prims, inst, inst_miss;
 };
 
 __device__ __forceinline__ uint32_t leaf_order(const DevScene& S, uint32_t ref) {
@@ -464,8 +464,10 @@ struct Traversal {
                     best.t = t;
                     best.prim = cur;
                     best.depth = level;
+                    if (level) {
 #pragma unroll
-                    for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) best.inst[k] = cur_inst[k];
+                        for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) best.inst[k] = cur_inst[k];
+                    }
                     ctx.put(level, pt, a_, b_, d);
                     // f32 upper bound of t with slack far above any f64 rounding discrepancy
                     float tf = (float)t;
@@ -480,6 +482,7 @@ struct Traversal {
             uint32_t inner = in->inner;
             if (inner != NRRT_REF_NONE && level < NRRT_MAX_INSTANCE_DEPTH) {
                 d3 no = o, nd = d;
+                if (COUNT) cnt->inst++;
                 instance_ray_inl(S, ii, no, nd);
                 Ray32 n32 = make_ray32(no, nd);
                 bool enter = true;
@@ -495,6 +498,7 @@ struct Traversal {
                     cur = inner;
                     return false;
                 }
+                if (COUNT) cnt->inst_miss++;
             }
         }
         // next pending entry; level markers are consumed on the way (leaving an instance rebuilds the parent-level

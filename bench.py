@@ -297,6 +297,22 @@ def run_b200(args):
         b_prim = 128 if d.n_planes >= d.n_spheres else 32   # bytes one exact primitive test reads (one record)
         b_state = 48 + 24 + 4 if mode == A.MODE_WAVEFRONT else 0  # extend kernel: ray in, hit out, queue index
         bytes_seg = nodes_seg * 64 + exact_seg * 48 + prims_seg * b_prim + b_state
+        # traversal-only microbenchmark (north_star's "traversal roofline"): coherent primary rays of the same camera
+        # through the fixed-ray entry point, no shading, no path state
+        Wc, Hc = cam.width, cam.height
+        xs, ys = np.meshgrid(np.arange(Wc, dtype=np.float64), np.arange(Hc, dtype=np.float64))
+        tl, du, dv = (np.array(list(v)) for v in (cam.viewport_top_left, cam.pixel_delta_u, cam.pixel_delta_v))
+        org = np.array(list(cam.look_from))
+        pts = tl + xs[..., None] * du + ys[..., None] * dv
+        prim_rays = torch.from_numpy(np.ascontiguousarray(
+            np.concatenate([np.broadcast_to(org, pts.shape), pts - org], axis=-1).reshape(-1, 6))).to(dev)
+        prim_hits = torch.zeros((prim_rays.shape[0], 112), dtype=torch.uint8, device=dev)
+        trav_best = 0.0
+        for _ in range(5):
+            ts = ctx.trace_rays_device(prim_rays.data_ptr(), prim_rays.shape[0], prim_hits.data_ptr())
+            trav_best = max(trav_best, prim_rays.shape[0] / ts["kernel_ms"] / 1e3)
+        del prim_rays, prim_hits
+        extend_rate = (my_segs / (ext_ms * 1e-3) / 1e6) if ext_ms > 0 else None
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -313,6 +329,10 @@ def run_b200(args):
             "exact_box_tests_per_segment": exact_seg, "segments_per_launch": my_segs / max(ext_launches, 1),
             "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": ext_launches,
             "kernel_share_of_step": ext_ms / sum_ms,
+            "extend_kernel_mrays_s": extend_rate,
+            "traversal_microbench_mrays_s": trav_best,
+            "frac_of_traversal_microbench": (extend_rate / trav_best) if extend_rate and trav_best else None,
+            "traversal_microbench": "coherent primary rays of the same camera through nrrt_trace_rays (no shading)",
             "note": "node/primitive fetches are L1/L2-resident by design (scene is KB-MB); the binding limit is "
                     "SM issue + FP64 pipe, see profiles/ for the ncu issue-slot figures",
         }
@@ -356,6 +376,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="wavefront", choices=["wavefront", "megakernel"])
+    ap.add_argument("--scene", default=SCENE, help="scene file (default: the benchmark workload)")
+    ap.add_argument("--depth", type=int, default=DEPTH)
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--spp", type=int, default=SPP)
@@ -363,6 +385,8 @@ def main():
     ap.add_argument("--ref-spp", type=int, default=32, help="spp per step of the --impl reference arm")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    global SCENE, WIDTH, HEIGHT, SPP, DEPTH
+    SCENE, WIDTH, HEIGHT, SPP, DEPTH = args.scene, args.width, args.height, args.spp, args.depth
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

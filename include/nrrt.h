@@ -299,14 +299,15 @@ enum {
     NRRT_TRACE_ORDERED = 0,    /* near-first traversal with conservative t-shrinking (render path) */
     NRRT_TRACE_VISIT_ALL = 1,  /* visit exactly the reference's node set (no shrinking)            */
     NRRT_TRACE_HOST_BUFFERS = 0,
-    NRRT_TRACE_DEVICE_BUFFERS = 2
+    NRRT_TRACE_DEVICE_BUFFERS = 2,
+    NRRT_TRACE_COUNT = 4       /* also fill node_visits / box_exact / prim_tests (per-ray atomics: slower) */
 };
 
 typedef struct nrrt_trace_stats {
-    uint64_t node_visits;   /* inner nodes fetched                 */
-    uint64_t box_exact;     /* f32-inconclusive box tests redone in f64 */
-    uint64_t prim_tests;    /* exact primitive tests               */
-    double kernel_ms;       /* CUDA-event time of the kernel       */
+    uint64_t node_visits;   /* NRRT_TRACE_COUNT: inner nodes fetched                 */
+    uint64_t box_exact;     /*   f32-inconclusive box tests redone in f64            */
+    uint64_t prim_tests;    /*   exact primitive tests                               */
+    double kernel_ms;       /* CUDA-event time of the kernel (always)                */
 } nrrt_trace_stats;
 
 /* BVH::hit (object.rs:89-121) for n rays: rays = n x {ox,oy,oz,dx,dy,dz}. */

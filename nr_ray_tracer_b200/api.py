@@ -149,17 +149,18 @@ class Context:
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
         out = np.zeros(rays.shape[0], dtype=A.HIT_DTYPE)
         st = A.TraceStats()
-        flags = A.TRACE_VISIT_ALL if visit_all else A.TRACE_ORDERED
+        flags = (A.TRACE_VISIT_ALL if visit_all else A.TRACE_ORDERED) | (A.TRACE_COUNT if want_stats else 0)
         self._check(lib().nrrt_trace_rays(self._h, rays.ctypes.data, rays.shape[0], tmin, tmax, flags, out.ctypes.data,
                                           C.byref(st) if want_stats else None))
         return out, {"node_visits": st.node_visits, "box_exact": st.box_exact, "prim_tests": st.prim_tests,
                      "kernel_ms": st.kernel_ms}
 
     def trace_rays_device(self, rays_ptr: int, n: int, out_ptr: int, tmin: float = 0.001, tmax: float = float("inf"),
-                          visit_all: bool = False):
+                          visit_all: bool = False, count: bool = False):
         """rays_ptr / out_ptr are device pointers (n x 6 f64, n x nrrt_hit)."""
         st = A.TraceStats()
-        flags = (A.TRACE_VISIT_ALL if visit_all else A.TRACE_ORDERED) | A.TRACE_DEVICE_BUFFERS
+        flags = (A.TRACE_VISIT_ALL if visit_all else A.TRACE_ORDERED) | A.TRACE_DEVICE_BUFFERS | \
+            (A.TRACE_COUNT if count else 0)
         self._check(lib().nrrt_trace_rays(self._h, C.c_void_p(rays_ptr), n, tmin, tmax, flags, C.c_void_p(out_ptr),
                                           C.byref(st)))
         return {"node_visits": st.node_visits, "box_exact": st.box_exact, "prim_tests": st.prim_tests,

@@ -801,7 +801,7 @@ int nrrt_trace_rays(nrrt_ctx* ctx, const double* rays, uint64_t n, double tmin, 
     CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     dim3 grid((unsigned)((n + NRRT_BLOCK - 1) / NRRT_BLOCK)), block(NRRT_BLOCK);
     size_t smem = (size_t)NRRT_BLOCK * NRRT_STACK_CAP * sizeof(uint32_t);
-    const bool count = stats != nullptr;
+    const bool count = stats != nullptr && (flags & NRRT_TRACE_COUNT) != 0;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (flags & NRRT_TRACE_VISIT_ALL) {
         if (count)

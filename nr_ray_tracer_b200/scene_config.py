@@ -237,6 +237,8 @@ def load_scene_file(path: str) -> Dict[str, Any]:
                 return tomllib.load(f)
     except OSError as e:
         raise SceneError(f"cannot read scene file {path}: {e}") from e
+    except (json.JSONDecodeError, tomllib.TOMLDecodeError) as e:
+        raise SceneError(f"cannot parse scene file {path}: {e}") from e
     raise SceneError("invalid scene file format!")
 
 

@@ -266,6 +266,36 @@ const char* nrrt_host_last_error(void);
 /* CameraBuilder::build (camera.rs:94-159). */
 int nrrt_host_camera_build(const nrrt_camera_config* config, nrrt_camera* out);
 
+/* ---- host side: native scene loader ---------------- */
+/* Mirror of the CLI's CameraConfig (cli.rs:157-270): every field optional; `present` says which were given.
+ * Angles in DEGREES here, like the CLI flags and the scene files (converted by nrrt_camera_file_to_config). */
+enum {
+    NRRT_CAM_WIDTH = 1 << 0, NRRT_CAM_HEIGHT = 1 << 1, NRRT_CAM_ASPECT_RATIO = 1 << 2, NRRT_CAM_BACKGROUND = 1 << 3,
+    NRRT_CAM_LOOK_AT = 1 << 4, NRRT_CAM_LOOK_FROM = 1 << 5, NRRT_CAM_VIEW_UP = 1 << 6, NRRT_CAM_FOV = 1 << 7,
+    NRRT_CAM_DEFOCUS = 1 << 8, NRRT_CAM_FOCUS = 1 << 9, NRRT_CAM_SPP = 1 << 10, NRRT_CAM_BOUNCES = 1 << 11
+};
+typedef struct nrrt_camera_file {
+    uint32_t present;
+    uint32_t width, height, samples_per_pixel, ray_max_bounces;
+    uint32_t _pad;
+    double aspect_ratio;
+    double background[3], look_at[3], look_from[3], view_up[3];
+    double field_of_view_deg, defocus_angle_deg, focus_distance;
+} nrrt_camera_file;
+
+typedef struct nrrt_loaded_scene nrrt_loaded_scene;
+/* SceneConfig::try_load_scene + try_build's object graph (scene_config.rs:411-492): .json / .toml by extension;
+ * paths inside the file (Image.path, Scene.path) resolve against base_dir (NULL = process CWD, like the
+ * reference).  JPEG textures are decoded natively (baseline).  NULL on error (nrrt_load_last_error). */
+nrrt_loaded_scene* nrrt_load_scene(const char* path, const char* base_dir);
+const nrrt_graph_desc* nrrt_loaded_graph(const nrrt_loaded_scene* scene); /* feed to nrrt_host_build */
+int nrrt_loaded_camera(const nrrt_loaded_scene* scene, nrrt_camera_file* out); /* the file's [camera] section */
+void nrrt_loaded_free(nrrt_loaded_scene* scene);
+const char* nrrt_load_last_error(void);
+/* CameraConfig::merge_with (cli.rs:316-355) and try_update onto CameraBuilder::default() (cli.rs:357-402). */
+void nrrt_camera_file_merge(nrrt_camera_file* base, const nrrt_camera_file* over);
+int nrrt_camera_file_to_config(const nrrt_camera_file* file, nrrt_camera_config* out);
+
 /* ---- device side -------------------------------------------------------- */
 typedef struct nrrt_ctx nrrt_ctx;
 
@@ -358,9 +388,16 @@ typedef void (*nrrt_progress_fn)(uint64_t pixels_done, uint64_t pixels_total, vo
 int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* camera, const nrrt_render_opts* opts,
                 float* out_rgb, nrrt_progress_fn progress, void* user, nrrt_render_stats* stats);
 
-/* sizeof() of the ABI structs as compiled (which = 0..15 in header order: object, material, texture,
+/* Output stage (§8(f) N2): gamma_correction (image.rs:53-57: p.powf(gamma) per channel, f32) followed by
+ * DynamicImage::to_rgb8 (render.rs:85-86: clamp to [0,1], x255, round) on the GPU, so only W*H*3 bytes cross PCIe.
+ * `rgb` is W*H*3 f32 (device pointer if NRRT_RENDER_OUT_DEVICE is set in flags, else host); `out_rgb8` is a
+ * caller-owned HOST buffer of W*H*3 bytes. */
+int nrrt_encode_rgb8(nrrt_ctx* ctx, const float* rgb, uint32_t width, uint32_t height, float gamma, uint32_t flags,
+                     uint8_t* out_rgb8);
+
+/* sizeof() of the ABI structs as compiled (which = 0..16 in header order: object, material, texture,
  * image, graph_desc, camera_config, camera, node, box, xform, instance, scene_desc, hit, trace_stats,
- * render_opts, render_stats) so a binding can verify its mirror of this header. */
+ * render_opts, render_stats, camera_file) so a binding can verify its mirror of this header. */
 size_t nrrt_abi_sizeof(int which);
 
 #ifdef __cplusplus

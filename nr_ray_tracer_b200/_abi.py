@@ -125,6 +125,16 @@ class RenderStats(C.Structure):
                 ("inst_misses", u64)]
 
 
+class CameraFile(C.Structure):
+    _fields_ = [("present", u32), ("width", u32), ("height", u32), ("samples_per_pixel", u32), ("ray_max_bounces", u32),
+                ("_pad", u32), ("aspect_ratio", f64), ("background", f64 * 3), ("look_at", f64 * 3),
+                ("look_from", f64 * 3), ("view_up", f64 * 3), ("field_of_view_deg", f64), ("defocus_angle_deg", f64),
+                ("focus_distance", f64)]
+
+
+CAM_WIDTH, CAM_HEIGHT, CAM_ASPECT_RATIO, CAM_BACKGROUND, CAM_LOOK_AT, CAM_LOOK_FROM, CAM_VIEW_UP, CAM_FOV, \
+    CAM_DEFOCUS, CAM_FOCUS, CAM_SPP, CAM_BOUNCES = (1 << i for i in range(12))
+
 PROGRESS_FN = C.CFUNCTYPE(None, u64, u64, C.c_void_p)
 
 # numpy dtype of nrrt_hit for zero-copy result arrays

@@ -46,6 +46,15 @@ def lib() -> C.CDLL:
         L.nrrt_host_free.argtypes = [C.c_void_p]
         L.nrrt_host_last_error.restype = C.c_char_p
         L.nrrt_host_camera_build.argtypes = [C.POINTER(A.CameraConfig), C.POINTER(A.Camera)]
+        L.nrrt_load_scene.restype = C.c_void_p
+        L.nrrt_load_scene.argtypes = [C.c_char_p, C.c_char_p]
+        L.nrrt_loaded_graph.restype = C.POINTER(A.GraphDesc)
+        L.nrrt_loaded_graph.argtypes = [C.c_void_p]
+        L.nrrt_loaded_camera.argtypes = [C.c_void_p, C.POINTER(A.CameraFile)]
+        L.nrrt_loaded_free.argtypes = [C.c_void_p]
+        L.nrrt_load_last_error.restype = C.c_char_p
+        L.nrrt_camera_file_merge.argtypes = [C.POINTER(A.CameraFile), C.POINTER(A.CameraFile)]
+        L.nrrt_camera_file_to_config.argtypes = [C.POINTER(A.CameraFile), C.POINTER(A.CameraConfig)]
         L.nrrt_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.nrrt_destroy.argtypes = [C.c_void_p]
         L.nrrt_last_error.restype = C.c_char_p
@@ -56,6 +65,7 @@ def lib() -> C.CDLL:
                                       C.c_void_p, C.POINTER(A.TraceStats)]
         L.nrrt_render.argtypes = [C.c_void_p, C.POINTER(A.Camera), C.POINTER(A.RenderOpts), C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.POINTER(A.RenderStats)]
+        L.nrrt_encode_rgb8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32, C.c_void_p]
         L.nrrt_abi_sizeof.restype = C.c_size_t
         L.nrrt_abi_sizeof.argtypes = [C.c_int]
         _lib = L
@@ -63,7 +73,7 @@ def lib() -> C.CDLL:
 
 
 ABI_STRUCTS = [A.Object, A.Material, A.Texture, A.Image, A.GraphDesc, A.CameraConfig, A.Camera, A.Node, A.Box,
-               A.Xform, A.Instance, A.SceneDesc, A.Hit, A.TraceStats, A.RenderOpts, A.RenderStats]
+               A.Xform, A.Instance, A.SceneDesc, A.Hit, A.TraceStats, A.RenderOpts, A.RenderStats, A.CameraFile]
 
 
 def camera_build(cfg: A.CameraConfig) -> A.Camera:
@@ -75,12 +85,51 @@ def camera_build(cfg: A.CameraConfig) -> A.Camera:
     return cam
 
 
+class NativeScene:
+    """Scene file loaded by the native C++ loader (csrc/scene_loader.cpp): graph description + [camera] section."""
+
+    def __init__(self, path: str, base_dir: Optional[str] = None):
+        self._h = lib().nrrt_load_scene(path.encode(), base_dir.encode() if base_dir else None)
+        if not self._h:
+            raise NrrtError(A.ERR_IO, lib().nrrt_load_last_error().decode())
+        self.graph = lib().nrrt_loaded_graph(self._h).contents
+        self.camera_file = A.CameraFile()
+        lib().nrrt_loaded_camera(self._h, C.byref(self.camera_file))
+
+    def camera_config(self, override: Optional[A.CameraFile] = None) -> A.CameraConfig:
+        """merge_with(override) then try_update onto the CameraBuilder defaults."""
+        merged = A.CameraFile.from_buffer_copy(bytes(self.camera_file))
+        if override is not None:
+            lib().nrrt_camera_file_merge(C.byref(merged), C.byref(override))
+        cfg = A.CameraConfig()
+        rc = lib().nrrt_camera_file_to_config(C.byref(merged), C.byref(cfg))
+        if rc != 0:
+            raise NrrtError(rc, "image size needs exactly two of width / height / aspect ratio")
+        return cfg
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().nrrt_loaded_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class HostScene:
     """Object graph -> reference BVH (objects/object.rs:41-73) -> flat device layout.  Pure host code."""
 
-    def __init__(self, graph: SceneGraph):
-        self._holder = graph.to_desc()
-        self._h = lib().nrrt_host_build(self._holder.ptr())
+    def __init__(self, graph):
+        """graph: a SceneGraph (Python loader) or a NativeScene (C++ loader)."""
+        if isinstance(graph, NativeScene):
+            self._holder = graph
+            self._h = lib().nrrt_host_build(C.byref(graph.graph))
+        else:
+            self._holder = graph.to_desc()
+            self._h = lib().nrrt_host_build(self._holder.ptr())
         if not self._h:
             raise NrrtError(A.ERR_INVALID, lib().nrrt_host_last_error().decode())
         self.desc = lib().nrrt_host_scene_desc(self._h).contents
@@ -189,6 +238,21 @@ class Context:
                                              "extend_launches", "pixels", "node_visits", "box_exact",
                                              "prim_tests", "inst_entries", "inst_misses")}
         return (None if out_device_ptr is not None else out), stats
+
+
+    def encode_rgb8(self, image: Optional[np.ndarray] = None, gamma: float = 0.5, device_ptr: Optional[int] = None,
+                    width: int = 0, height: int = 0) -> np.ndarray:
+        """gamma_correction + to_rgb8 (render.rs:83-87) on the GPU -> (H, W, 3) uint8.  Default gamma 0.5 is the
+        CLI's DEFAULT_IMAGE_GAMMA_VALUE (constants.rs:1)."""
+        if device_ptr is not None:
+            h, w, ptr, flags = height, width, C.c_void_p(device_ptr), A.RENDER_OUT_DEVICE
+        else:
+            image = np.ascontiguousarray(image, dtype=np.float32)
+            h, w = image.shape[0], image.shape[1]
+            ptr, flags = C.c_void_p(image.ctypes.data), 0
+        out = np.zeros((h, w, 3), dtype=np.uint8)
+        self._check(lib().nrrt_encode_rgb8(self._h, ptr, w, h, gamma, flags, C.c_void_p(out.ctypes.data)))
+        return out
 
 
 class Scene:

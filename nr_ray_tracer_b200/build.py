@@ -9,8 +9,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnrrt_b200.so")
-SOURCES = ["nrrt_device.cu", "host_scene.cpp"]
-HEADERS = ["rt_device.cuh", "host_math.hpp", os.path.join("..", "..", "include", "nrrt.h")]
+CLI = os.path.join(HERE, "bin", "nr-ray-tracer")
+SOURCES = ["nrrt_device.cu", "host_scene.cpp", "scene_loader.cpp"]
+HEADERS = ["rt_device.cuh", "host_math.hpp", "jpeg_baseline.hpp", os.path.join("..", "..", "include", "nrrt.h")]
 
 
 def _nvcc() -> str:
@@ -22,6 +23,8 @@ def _nvcc() -> str:
 
 def needs_build() -> bool:
     if not os.path.exists(LIB):
+        return True
+    if not os.path.exists(CLI) or os.path.getmtime(CLI) < os.path.getmtime(os.path.join(CSRC, "cli_main.cpp")):
         return True
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
@@ -42,7 +45,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stdout + r.stderr)
+    build_cli(host_cxx)
     return LIB
+
+
+def build_cli(host_cxx: str = "/usr/bin/g++") -> str:
+    """`nr-ray-tracer render ...` (csrc/cli_main.cpp) linked against the in-tree library."""
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    cmd = [host_cxx, "-O2", "-std=c++17", os.path.join(CSRC, "cli_main.cpp"), "-o", CLI, "-L" + HERE, "-lnrrt_b200",
+           "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building the CLI failed:\n" + r.stdout + r.stderr)
+    return CLI
 
 
 if __name__ == "__main__":

@@ -269,6 +269,16 @@ __global__ void k_resolve(const __grid_constant__ nrrt_camera cam, const __grid_
     out[ob] = (float)col.x, out[ob + 1] = (float)col.y, out[ob + 2] = (float)col.z;
 }
 
+// output stage: gamma_correction (image.rs:53-57) + to_rgb8 (clamp, x255, round) — §8(f) N2
+__global__ void k_encode_rgb8(const float* __restrict__ rgb, size_t n, float gamma, uint8_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = powf(rgb[i], gamma);
+    v = fminf(fmaxf(v, 0.0f), 1.0f);       // f32::clamp; NaN stays NaN and casts to 0 like NumCast would reject -> 0
+    float q = roundf(v * 255.0f);          // f32::round: half away from zero
+    out[i] = (v == v) ? (uint8_t)q : (uint8_t)0;
+}
+
 // ------------------------------------------------------------------ wavefront
 // SoA path state, one entry per slot (n = n_slots).
 struct WfState {
@@ -1086,6 +1096,44 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     return NRRT_OK;
 }
 
+int nrrt_encode_rgb8(nrrt_ctx* ctx, const float* rgb, uint32_t width, uint32_t height, float gamma, uint32_t flags,
+                     uint8_t* out_rgb8) {
+    if (!ctx) return NRRT_ERR_INVALID;
+    if (!rgb || !out_rgb8 || width == 0 || height == 0) {
+        ctx->err = "nrrt_encode_rgb8: bad arguments";
+        return NRRT_ERR_INVALID;
+    }
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)width * height * 3;
+    const bool in_dev = (flags & NRRT_RENDER_OUT_DEVICE) != 0;
+    // the render scratch may hold a framebuffer the caller passed back in; carve above it
+    size_t need = ((n + 255) & ~(size_t)255) + (in_dev ? 0 : n * sizeof(float) + 256);
+    void* tmp = nullptr;
+    CK(cudaMalloc(&tmp, need));
+    uint8_t* d_out = (uint8_t*)tmp;
+    const float* d_in = rgb;
+    if (!in_dev) {
+        float* staged = (float*)((char*)tmp + ((n + 255) & ~(size_t)255));
+        cudaError_t e = cudaMemcpyAsync(staged, rgb, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+            cudaFree(tmp);
+            ctx->err = std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e);
+            return NRRT_ERR_CUDA;
+        }
+        d_in = staged;
+    }
+    k_encode_rgb8<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_in, n, gamma, d_out);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_rgb8, d_out, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("nrrt_encode_rgb8: ") + cudaGetErrorString(e);
+        return NRRT_ERR_CUDA;
+    }
+    return NRRT_OK;
+}
+
 // struct sizes, so bindings can verify their mirror of the header
 size_t nrrt_abi_sizeof(int which) {
     switch (which) {
@@ -1105,6 +1153,7 @@ size_t nrrt_abi_sizeof(int which) {
         case 13: return sizeof(nrrt_trace_stats);
         case 14: return sizeof(nrrt_render_opts);
         case 15: return sizeof(nrrt_render_stats);
+        case 16: return sizeof(nrrt_camera_file);
         default: return 0;
     }
 }

@@ -266,6 +266,56 @@ def test_full_size_properties_1080p(gpu_ctx):
     del hs
 
 
+def test_output_stage_gamma_and_rgb8_matches_host_definition(gpu_ctx):
+    """§8(f) N2: gamma_correction (image.rs:53-57) + to_rgb8 (clamp, x255, round) on the GPU vs the same formula in
+    numpy f32.  powf differs by <= 2 ulp between CUDA and libm, so a value sitting on a rounding boundary may land one
+    code away: tolerance = at most 1 LSB, on at most 0.1 % of the values."""
+    g = load("cornell-box-scene.json", width=160, height=90, samples_per_pixel=16)
+    hs = _scene(gpu_ctx, g)
+    img, _ = gpu_ctx.render(api.camera_build(g.camera.to_builder_config()), seed=3)
+    img[0, 0] = [0.0, 1.0, 7.5]          # exact ends and an over-range value
+    img[0, 1] = [0.25, 0.5, 1e-8]
+    for gamma in (0.5, 1.0, 0.4545):
+        got = gpu_ctx.encode_rgb8(img, gamma=gamma)
+        ref = np.floor(np.clip(np.power(img, np.float32(gamma), dtype=np.float32), 0, 1) * np.float32(255) + np.float32(0.5)).astype(np.uint8)
+        diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() <= 1e-3, (gamma, diff.max(), (diff > 0).mean())
+        assert got[0, 0].tolist() == [0, 255, 255]
+    assert gpu_ctx.encode_rgb8(img, gamma=0.5)[0, 1, 0] == 128 and gpu_ctx.encode_rgb8(img, gamma=1.0)[0, 1, 1] == 128
+    del hs
+
+
+def test_cli_render_matches_library_path(gpu_ctx, tmp_path):
+    """The native CLI (`nr-ray-tracer render`, mirror of commands/render.rs:104-115) end to end: native loader ->
+    host BVH build -> GPU render -> GPU gamma/rgb8 -> PNG, against the Python-driven path on the same scene."""
+    import subprocess
+    from PIL import Image
+    from nr_ray_tracer_b200 import build as B
+    B.build()
+    out = tmp_path / "cli.png"
+    cmd = [B.CLI, "render", "scenes/cornell-box-scene.json", "-W", "96", "-H", "54", "--samples-per-pixel", "8",
+           "--seed", "5", "-o", str(out), "-v"]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stderr
+    assert "Mrays/s" in r.stdout
+    got = np.asarray(Image.open(out).convert("RGB"))
+    g = load("cornell-box-scene.json", width=96, height=54, samples_per_pixel=8)
+    hs = _scene(gpu_ctx, g)
+    img, _ = gpu_ctx.render(api.camera_build(g.camera.to_builder_config()), seed=5)
+    ref = gpu_ctx.encode_rgb8(img, gamma=0.5)
+    assert np.array_equal(got, ref)
+    # refuses to overwrite without -f (ImageConfig::get_file, cli.rs:140-154), accepts env fallbacks and .ppm
+    r2 = subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r2.returncode != 0
+    ppm = tmp_path / "env.ppm"
+    env = dict(os.environ, NR_RT_CAMERA_WIDTH="32", NR_RT_CAMERA_HEIGHT="18", NR_RT_CAMERA_SAMPLES_PER_PIXEL="2")
+    r3 = subprocess.run([B.CLI, "render", "scenes/quads.toml", "-o", str(ppm)], capture_output=True, text=True, env=env,
+                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r3.returncode == 0, r3.stderr
+    assert Image.open(ppm).size == (32, 18)
+    del hs
+
+
 def test_errors_are_reported_not_swallowed(gpu_ctx):
     ctx = api.Context(0)
     cam = api.camera_build(load("quads.toml", width=8, height=8).camera.to_builder_config())

@@ -370,6 +370,7 @@ def run_b200(args):
 
 
 def main():
+    global SCENE, WIDTH, HEIGHT, SPP, DEPTH
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -385,7 +386,6 @@ def main():
     ap.add_argument("--ref-spp", type=int, default=32, help="spp per step of the --impl reference arm")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    global SCENE, WIDTH, HEIGHT, SPP, DEPTH
     SCENE, WIDTH, HEIGHT, SPP, DEPTH = args.scene, args.width, args.height, args.spp, args.depth
     if args.impl == "reference":
         return run_reference(args)

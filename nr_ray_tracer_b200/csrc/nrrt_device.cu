@@ -139,14 +139,17 @@ k_trace_rays(const __grid_constant__ DevScene S, const double* __restrict__ rays
 
 // One step of Camera::get_ray_color (camera.rs:269-300) in iterative form:  L += T*emitted; T *= color.
 // Returns true while the path is alive.
+template <uint32_t F = NRRT_F_ALL>
 __device__ __forceinline__ uint32_t hit_material(const DevScene& S, uint32_t prim) {
-    return NRRT_REF_TYPE(prim) == NRRT_REF_SPHERE ? S.sphere_material[NRRT_REF_INDEX(prim)]
-                                                  : (S.plane_material[NRRT_REF_INDEX(prim)] & ~NRRT_PLANE_TRIANGLE_BIT);
+    if ((F & NRRT_F_SPHERES) && (!(F & NRRT_F_PLANES) || NRRT_REF_TYPE(prim) == NRRT_REF_SPHERE))
+        return S.sphere_material[NRRT_REF_INDEX(prim)];
+    return S.plane_material[NRRT_REF_INDEX(prim)] & ~NRRT_PLANE_TRIANGLE_BIT;
 }
+template <uint32_t F = NRRT_F_ALL>
 __device__ __forceinline__ bool path_shade(const DevScene& S, const nrrt_camera& cam, const HitRec& rec,
                                            const Sampler& smp, d3& o, d3& d, d3& T, d3& L, uint32_t& bounce) {
     d3 emitted, atten, nd;
-    bool cont = shade_hit(S, rec, d, bounce == 0, smp, bounce + 1, emitted, atten, nd);
+    bool cont = shade_hit<F>(S, rec, d, bounce == 0, smp, bounce + 1, emitted, atten, nd);
     L = add3(L, mul3(T, emitted));
     if (!cont) return false;
     T = mul3(T, atten);
@@ -339,6 +342,7 @@ k_wf_init(const __grid_constant__ nrrt_camera cam, const __grid_constant__ Rende
 #ifndef NRRT_REFILL_MIN
 #define NRRT_REFILL_MIN 16  // refill once this many lanes of the warp are idle (8/16 measured: 16 wins on Cornell + teapot)
 #endif
+template <uint32_t F>
 __global__ void __launch_bounds__(NRRT_BLOCK, 5)
 k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState W, uint32_t n, uint32_t qin) {
     extern __shared__ uint32_t s_stack[];
@@ -348,7 +352,7 @@ k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState 
         W.count[qin ^ 1] = 0;   // the other queue is filled by the next shade pass
         W.cursor[qin ^ 1] = 0;  // and consumed by the next extend pass
     }
-    Traversal<false, false> tr;
+    Traversal<false, false, F> tr;
     bool has = false, exhausted = false;
     uint32_t slot = 0;
     for (;;) {
@@ -373,8 +377,8 @@ k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState 
                      has) && has) {
             W.hit_t[slot] = tr.best.t;
             W.hit_prim[slot] = tr.best.prim;
-            W.hit_inst[slot] = tr.best.depth | (tr.best.inst[0] << 3);
-            if (tr.best.depth > 1)
+            if (F & NRRT_F_INSTANCES) W.hit_inst[slot] = tr.best.depth | (tr.best.inst[0] << 3);
+            if ((F & NRRT_F_INSTANCES) && tr.best.depth > 1)
                 for (uint32_t l = 1; l < tr.best.depth; ++l) W.hit_inst[(size_t)l * n + slot] = tr.best.inst[l];
             has = false;
         }
@@ -385,6 +389,7 @@ k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState 
 #ifndef NRRT_SHADE_MINBLOCKS
 #define NRRT_SHADE_MINBLOCKS 5
 #endif
+template <uint32_t F>
 __global__ void __launch_bounds__(NRRT_BLOCK, NRRT_SHADE_MINBLOCKS)
 k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_camera cam,
            const __grid_constant__ RenderParams P, const __grid_constant__ WfState W, uint32_t qin) {
@@ -413,12 +418,12 @@ k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_came
         h.t = W.hit_t[slot];
         h.prim = W.hit_prim[slot];
         {
-            const uint32_t w0 = (h.prim == NRRT_REF_NONE) ? 0u : W.hit_inst[slot];
+            const uint32_t w0 = (!(F & NRRT_F_INSTANCES) || h.prim == NRRT_REF_NONE) ? 0u : W.hit_inst[slot];
             h.depth = w0 & 7u;
             h.inst[0] = w0 >> 3;
 #pragma unroll
             for (uint32_t l = 1; l < NRRT_MAX_INSTANCE_DEPTH; ++l)
-                h.inst[l] = (l < h.depth) ? W.hit_inst[(size_t)l * n + slot] : 0u;
+                h.inst[l] = ((F & NRRT_F_INSTANCES) && l < h.depth) ? W.hit_inst[(size_t)l * n + slot] : 0u;
         }
 #if !NRRT_HIT_SINK
         survive = path_step(S, cam, h, smp, o, d, T, L, bounce);
@@ -431,10 +436,13 @@ k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_came
             const double* A = W.hit_attr;
             d3 p_obj = mk3(A[slot], A[(size_t)n + slot], A[2 * (size_t)n + slot]);
             d3 d_dir = d;
-            if (h.depth) d_dir = mk3(A[5 * (size_t)n + slot], A[6 * (size_t)n + slot], A[7 * (size_t)n + slot]);
-            resolve_hit_attr(S, h, p_obj, A[3 * (size_t)n + slot], A[4 * (size_t)n + slot], d_dir,
-                             (S.material_flags[hit_material(S, h.prim)] & 1u) != 0, rec);
-            survive = path_shade(S, cam, rec, smp, o, d, T, L, bounce);
+            if ((F & NRRT_F_INSTANCES) && h.depth)
+                d_dir = mk3(A[5 * (size_t)n + slot], A[6 * (size_t)n + slot], A[7 * (size_t)n + slot]);
+            double al = 0.0, be = 0.0;
+            if (F & NRRT_F_PLANES) al = A[3 * (size_t)n + slot], be = A[4 * (size_t)n + slot];
+            const bool want_uv = (F & NRRT_F_TEXTURED) && (S.material_flags[hit_material<F>(S, h.prim)] & 1u) != 0;
+            resolve_hit_attr<F>(S, h, p_obj, al, be, d_dir, want_uv, rec);
+            survive = path_shade<F>(S, cam, rec, smp, o, d, T, L, bounce);
         }
 #endif
         if (!survive) {  // path finished: add it to the item's partial sum (sample order)
@@ -516,6 +524,7 @@ struct nrrt_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     unsigned persistent_blocks = 592;  // SMs x resident blocks of the extend kernel
+    uint32_t features = NRRT_F_ALL;    // NRRT_F_* mask of the uploaded scene
 };
 
 #define CK(call)                                                                                   \
@@ -636,6 +645,8 @@ int nrrt_set_stream(nrrt_ctx* ctx, void* cuda_stream) {
     ctx->stream = (cudaStream_t)cuda_stream;
     return NRRT_OK;
 }
+
+static uint32_t pick_features(uint32_t need);
 
 int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
     if (!ctx || !sc) return NRRT_ERR_INVALID;
@@ -765,10 +776,49 @@ int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
     D.n_nodes = sc->n_nodes, D.n_spheres = sc->n_spheres, D.n_planes = sc->n_planes;
     D.n_instances = sc->n_instances, D.n_materials = sc->n_materials, D.n_textures = sc->n_textures;
     CK(cudaStreamSynchronize(ctx->stream));  // host staging vectors die at return
+    {
+        uint32_t need = 0;
+        if (sc->n_spheres) need |= NRRT_F_SPHERES;
+        if (sc->n_planes) need |= NRRT_F_PLANES;
+        if (sc->n_instances) need |= NRRT_F_INSTANCES;
+        for (uint32_t i = 0; i < sc->n_textures; ++i)
+            if (sc->textures[i].kind != NRRT_TEX_SOLID) need |= NRRT_F_TEXTURED;
+        for (uint32_t i = 0; i < sc->n_materials; ++i)
+            if (sc->materials[i].kind == NRRT_MAT_DIELECTRIC) need |= NRRT_F_DIELECTRIC;
+        ctx->features = pick_features(need);
+    }
     ctx->dev = D;
     ctx->max_stack = sc->max_stack;
     ctx->has_scene = true;
     return NRRT_OK;
+}
+
+// Kernel instantiations by scene features (see NRRT_F_* in rt_device.cuh): the three shapes the shipped scenes
+// have, plus the general one.
+#define NRRT_F_CORNELL (NRRT_F_PLANES | NRRT_F_INSTANCES)                 // planar scenes with wrappers, solid colours
+#define NRRT_F_BALLS (NRRT_F_SPHERES | NRRT_F_DIELECTRIC)                  // sphere fields, solid colours
+#define NRRT_F_BALLS_TEX (NRRT_F_SPHERES | NRRT_F_TEXTURED)                // textured spheres (earth, noise)
+static uint32_t pick_features(uint32_t need) {
+    for (uint32_t cand : {NRRT_F_CORNELL, NRRT_F_BALLS, NRRT_F_BALLS_TEX})
+        if ((need & ~cand) == 0) return cand;
+    return NRRT_F_ALL;
+}
+static void launch_extend(nrrt_ctx* ctx, unsigned blocks, size_t smem, const WfState& Wf, uint32_t n, uint32_t qin) {
+    switch (ctx->features) {
+        case NRRT_F_CORNELL: k_wf_extend<NRRT_F_CORNELL><<<blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, Wf, n, qin); break;
+        case NRRT_F_BALLS: k_wf_extend<NRRT_F_BALLS><<<blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, Wf, n, qin); break;
+        case NRRT_F_BALLS_TEX: k_wf_extend<NRRT_F_BALLS_TEX><<<blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, Wf, n, qin); break;
+        default: k_wf_extend<NRRT_F_ALL><<<blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, Wf, n, qin); break;
+    }
+}
+static void launch_shade(nrrt_ctx* ctx, unsigned blocks, const nrrt_camera& c, const RenderParams& P, const WfState& Wf,
+                         uint32_t qin) {
+    switch (ctx->features) {
+        case NRRT_F_CORNELL: k_wf_shade<NRRT_F_CORNELL><<<blocks, NRRT_BLOCK, 0, ctx->stream>>>(ctx->dev, c, P, Wf, qin); break;
+        case NRRT_F_BALLS: k_wf_shade<NRRT_F_BALLS><<<blocks, NRRT_BLOCK, 0, ctx->stream>>>(ctx->dev, c, P, Wf, qin); break;
+        case NRRT_F_BALLS_TEX: k_wf_shade<NRRT_F_BALLS_TEX><<<blocks, NRRT_BLOCK, 0, ctx->stream>>>(ctx->dev, c, P, Wf, qin); break;
+        default: k_wf_shade<NRRT_F_ALL><<<blocks, NRRT_BLOCK, 0, ctx->stream>>>(ctx->dev, c, P, Wf, qin); break;
+    }
 }
 
 static int ensure_scratch(nrrt_ctx* ctx, size_t bytes) {
@@ -1006,13 +1056,12 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
                 ta = ctx->ev_pool[RING + 2 * timing.size()], tb = ctx->ev_pool[RING + 2 * timing.size() + 1];
                 CK(cudaEventRecord(ta, ctx->stream));
             }
-            k_wf_extend<<<std::min<unsigned>(work_blocks, ctx->persistent_blocks), NRRT_BLOCK, smem, ctx->stream>>>(
-                ctx->dev, Wf, (uint32_t)n, qin);
+            launch_extend(ctx, std::min<unsigned>(work_blocks, ctx->persistent_blocks), smem, Wf, (uint32_t)n, qin);
             if (timed) {
                 CK(cudaEventRecord(tb, ctx->stream));
                 timing.emplace_back(ta, tb);
             }
-            k_wf_shade<<<work_blocks, NRRT_BLOCK, 0, ctx->stream>>>(ctx->dev, c, P, Wf, qin);
+            launch_shade(ctx, work_blocks, c, P, Wf, qin);
             CK(cudaGetLastError());
             launches += 2;
             ++extend_launches;

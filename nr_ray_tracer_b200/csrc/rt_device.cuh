@@ -22,6 +22,15 @@
 #ifndef NRRT_HIT_SINK
 #define NRRT_HIT_SINK 1    // 1: the wavefront traverse kernel hands hit attributes to the shade kernel
 #endif
+// Scene features a kernel instantiation has to handle.  nrrt_scene_upload computes the mask of the uploaded scene
+// and the render path picks the tightest instantiation, so e.g. the Cornell box runs kernels without sphere,
+// image, noise or dielectric code and spheres.toml runs kernels without any instance machinery.
+#define NRRT_F_SPHERES 1u
+#define NRRT_F_PLANES 2u
+#define NRRT_F_INSTANCES 4u
+#define NRRT_F_TEXTURED 8u      // any non-solid texture (checker / image / noise / marble)
+#define NRRT_F_DIELECTRIC 16u
+#define NRRT_F_ALL 31u
 #define NRRT_STACK_CAP 32          // traversal stack entries per thread (host validates max_stack)
 #define NRRT_REF_POP 0xC0000000u   // type 6: "leave instance level" marker on the stack
 #define NRRT_INF __longlong_as_double(0x7ff0000000000000LL)
@@ -348,7 +357,7 @@ struct MemCtx {
 // round() must be called by ALL 32 lanes of the warp (lanes without a query pass has = false); it returns true
 // when the lane's query is finished.  Keeping the state resumable lets a persistent warp swap finished rays for
 // fresh ones between rounds.
-template <bool VISIT_ALL, bool COUNT>
+template <bool VISIT_ALL, bool COUNT, uint32_t F = NRRT_F_ALL>
 struct Traversal {
     d3 o, d;         // ray in the current space (world, or the object space of the innermost entered instance)
     Ray32 r32;
@@ -436,22 +445,25 @@ struct Traversal {
         }
         // ---------------- phase 2: the warp votes for one kind of leaf
         const uint32_t ty = has ? NRRT_REF_TYPE(cur) : (uint32_t)NRRT_REF_EMPTY;
-        const bool is_prim = (ty == NRRT_REF_SPHERE || ty == NRRT_REF_PLANE), is_inst = (ty == NRRT_REF_INSTANCE);
-        const unsigned m_prim = __ballot_sync(0xffffffffu, is_prim), m_inst = __ballot_sync(0xffffffffu, is_inst);
-        if (!has) return true;
+        const bool is_prim = ((F & NRRT_F_SPHERES) && ty == NRRT_REF_SPHERE) || ((F & NRRT_F_PLANES) && ty == NRRT_REF_PLANE);
+        const bool is_inst = (F & NRRT_F_INSTANCES) && ty == NRRT_REF_INSTANCE;
+        bool serve_inst = false;
+        if (F & NRRT_F_INSTANCES) {  // scenes without wrappers have nothing to vote on
 #if NRRT_LEAF_VOTE
-        const bool serve_inst = __popc(m_inst) > __popc(m_prim);
+            const unsigned m_prim = __ballot_sync(0xffffffffu, is_prim), m_inst = __ballot_sync(0xffffffffu, is_inst);
+            serve_inst = __popc(m_inst) > __popc(m_prim);
 #else
-        const bool serve_inst = is_inst;  // no vote: every lane processes whatever leaf it holds
-        (void)m_prim, (void)m_inst;
+            serve_inst = is_inst;  // no vote: every lane processes whatever leaf it holds
 #endif
+        }
+        if (!has) return true;
         if (is_prim) {
             if (serve_inst) return false;  // wait: this round enters instances
             if (COUNT) cnt->prims++;
             double a_ = 0.0, b_ = 0.0;
             d3 pt;
             double t;
-            if (ty == NRRT_REF_SPHERE) {
+            if ((F & NRRT_F_SPHERES) && (!(F & NRRT_F_PLANES) || ty == NRRT_REF_SPHERE)) {
                 t = sphere_t(S, NRRT_REF_INDEX(cur), o, d, tmin, tmax);
                 pt = ray_at(o, d, t);
             } else {
@@ -464,7 +476,7 @@ struct Traversal {
                     best.t = t;
                     best.prim = cur;
                     best.depth = level;
-                    if (level) {
+                    if ((F & NRRT_F_INSTANCES) && level) {
 #pragma unroll
                         for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) best.inst[k] = cur_inst[k];
                     }
@@ -503,7 +515,7 @@ struct Traversal {
         }
         // next pending entry; level markers are consumed on the way (leaving an instance rebuilds the parent-level
         // ray from the world ray: a bit-identical recomputation).  Phase 1 may already have popped a marker.
-        bool in_hand = (cur == NRRT_REF_POP);
+        bool in_hand = (F & NRRT_F_INSTANCES) && (cur == NRRT_REF_POP);
         for (;;) {
             if (!in_hand) {
                 if (sp == 0) {
@@ -514,7 +526,7 @@ struct Traversal {
                 cur = stack[sp * sstride];
             }
             in_hand = false;
-            if (cur != NRRT_REF_POP) return false;
+            if (!(F & NRRT_F_INSTANCES) || cur != NRRT_REF_POP) return false;
             --level;
             ctx.get(o, d);
             for (uint32_t l = 0; l < level; ++l) instance_ray(S, cur_inst[l], o, d);
@@ -589,16 +601,17 @@ __device__ __forceinline__ void resolve_hit(const DevScene& S, const HitId& h, d
 // Same HitRecord, from the attributes the wavefront traverse kernel stored when the candidate won (MemHitSink):
 // p_obj / alpha / beta are the very values the primitive test computed, d_dir is the ray direction in the
 // primitive's space (the world direction for depth 0).
+template <uint32_t F = NRRT_F_ALL>
 __device__ __forceinline__ void resolve_hit_attr(const DevScene& S, const HitId& h, d3 p_obj, double alpha, double beta,
                                                  d3 d_dir, bool want_uv, HitRec& rec) {
     uint32_t ty = NRRT_REF_TYPE(h.prim), ix = NRRT_REF_INDEX(h.prim);
     d3 point = p_obj, outward;
     double u = alpha, v = beta;
-    if (ty == NRRT_REF_SPHERE) {
+    if ((F & NRRT_F_SPHERES) && (!(F & NRRT_F_PLANES) || ty == NRRT_REF_SPHERE)) {
         d3 c = ld3(S.sphere_rec + 4 * (size_t)ix);
         outward = normalize3(sub3(point, c));  // sphere.rs:151
         u = 0.0, v = 0.0;
-        if (want_uv) {                         // sphere.rs:153-159
+        if ((F & NRRT_F_TEXTURED) && want_uv) {  // sphere.rs:153-159
             const double PI = 3.14159265358979323846264338327950288;
             double theta = acos(-outward.y);
             double phi = xadd(atan2(-outward.z, outward.x), PI);
@@ -613,7 +626,8 @@ __device__ __forceinline__ void resolve_hit_attr(const DevScene& S, const HitId&
     double sign = signum(dot3(d_dir, outward));
     rec.front_face = sign < 0.0;
     d3 normal = scale3(outward, -sign);
-    for (uint32_t l = h.depth; l-- > 0;) instance_hit_back(S, h.inst[l], point, normal);
+    if (F & NRRT_F_INSTANCES)
+        for (uint32_t l = h.depth; l-- > 0;) instance_hit_back(S, h.inst[l], point, normal);
     rec.point = point;
     rec.normal = normal;
     rec.u = u;
@@ -748,7 +762,9 @@ __device__ __forceinline__ uint32_t sat_u32(double x) {  // Rust `as u32`
 }
 
 // Texture::get_color (textures/*.rs).  Checker recursion is a loop: sub-textures always precede.
+template <uint32_t F = NRRT_F_ALL>
 __device__ __forceinline__ d3 texture_color(const DevScene& S, uint32_t tex, double u, double v, d3 point) {
+    if (!(F & NRRT_F_TEXTURED)) return ld3(S.textures[tex].color);  // every texture of the scene is a SolidColor
     for (int guard = 0; guard < 64; ++guard) {
         const nrrt_texture* t = &S.textures[tex];
         uint32_t kind = t->kind;
@@ -782,6 +798,7 @@ __device__ __forceinline__ d3 texture_color(const DevScene& S, uint32_t tex, dou
 
 // --------------------------------------------------------------------------- materials
 // Returns true if the path continues.  emitted is always set (material.rs:20-26, diffuse_light.rs:63-75).
+template <uint32_t F = NRRT_F_ALL>
 __device__ __forceinline__ bool shade_hit(const DevScene& S, const HitRec& h, d3 rd, bool primary, const Sampler& smp,
                                           uint32_t stage, d3& emitted, d3& atten, d3& new_dir) {
     const nrrt_material* m = &S.materials[h.material];
@@ -795,7 +812,7 @@ __device__ __forceinline__ bool shade_hit(const DevScene& S, const HitRec& h, d3
         d3 dir = add3(h.normal, rnd);
         if (fabs(dir.x) < 1e-8 && fabs(dir.y) < 1e-8 && fabs(dir.z) < 1e-8) dir = h.normal;
         new_dir = dir;
-        atten = texture_color(S, m->texture, h.u, h.v, h.point);
+        atten = texture_color<F>(S, m->texture, h.u, h.v, h.point);
         return true;
     }
     if (kind == NRRT_MAT_METAL) {  // metal.rs:73-91
@@ -803,12 +820,12 @@ __device__ __forceinline__ bool shade_hit(const DevScene& S, const HitRec& h, d3
         d3 dir = add3(normalize3(refl), scale3(rnd, m->param));
         if (dot3(dir, h.normal) > 0.0) {
             new_dir = dir;
-            atten = texture_color(S, m->texture, h.u, h.v, h.point);
+            atten = texture_color<F>(S, m->texture, h.u, h.v, h.point);
             return true;
         }
         return false;
     }
-    if (kind == NRRT_MAT_DIELECTRIC) {  // dielectric.rs:39-67
+    if ((F & NRRT_F_DIELECTRIC) && kind == NRRT_MAT_DIELECTRIC) {  // dielectric.rs:39-67
         double ri = h.front_face ? xdiv(1.0, m->param) : m->param;
         d3 unit = normalize3(rd);
         double cos_theta = fmin(dot3(neg3(unit), h.normal), 1.0);
@@ -838,7 +855,7 @@ __device__ __forceinline__ bool shade_hit(const DevScene& S, const HitRec& h, d3
     }
     // DiffuseLight: emits, never scatters.  Seen by a camera ray it shows at x1 (quirk Q3).
     double k = primary ? 1.0 : m->param;
-    emitted = scale3(texture_color(S, m->texture, h.u, h.v, h.point), k);
+    emitted = scale3(texture_color<F>(S, m->texture, h.u, h.v, h.point), k);
     return false;
 }
 

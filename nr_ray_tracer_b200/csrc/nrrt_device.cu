@@ -22,6 +22,13 @@
 #include "rt_device.cuh"
 
 #define NRRT_BLOCK 128
+#ifndef NRRT_SPLIT_QUEUE
+#define NRRT_SPLIT_QUEUE 0  // 1: camera rays and bounce rays occupy separate regions of the ray queue.
+// Measured on B200 (round 1): splitting is 3.4x SLOWER (Cornell 3439 -> 994 Mseg/s, earth 4941 -> 1263).  With one
+// queue every slot survives every pass (in-slot regeneration), so the queue stays in near-ascending slot order and
+// the SoA path state is read and written coalesced; splitting it re-partitions the order every pass until the 32
+// slots of a warp are scattered and each 8-byte access costs a 32-byte sector.  Kept as a switch for the record.
+#endif
 
 // =========================================================================== kernels
 // Work decomposition.  A work item is (owned pixel, sample chunk): the pixel's samples
@@ -298,11 +305,20 @@ struct WfState {
     uint32_t* hit_inst;   // [MAX_DEPTH][n]: word 0 = depth | inst[0] << 3, words 1.. = inst[1..] (depth >= 2 only)
     double* hit_attr;     // [8][n]: object-space hit point, alpha, beta, object-space direction (MemHitSink)
     uint32_t* queue[2];   // [n] slot indices
-    uint32_t* count;      // [2] queue lengths
+    uint32_t* count;      // [2][2] queue lengths: [q][0] = bounce rays, stored at the front of queue q in ascending
+                          //        order; [q][1] = freshly generated camera rays, stored from the back in descending
+                          //        order.  Camera rays of neighbouring pixels are coherent; keeping them in warps
+                          //        of their own (instead of mixing them with incoherent bounce rays) keeps those
+                          //        warps converged in the traverse and shade kernels.
     uint32_t* cursor;     // [2] fetch cursors of the persistent extend kernel
     double* partials;     // [n_items][3]
     unsigned long long* counters;  // [0]=segments [1]=paths [5]=next work item
 };
+
+// logical queue position i in [0, n_bounce + n_cam) -> physical index in the queue array of n entries
+__device__ __forceinline__ uint32_t queue_slot(const uint32_t* q, uint32_t n, uint32_t n_bounce, uint32_t i) {
+    return q[i < n_bounce ? i : n - 1u - (i - n_bounce)];
+}
 
 // ray generation for the initial items
 __global__ void __launch_bounds__(NRRT_BLOCK)
@@ -310,8 +326,10 @@ k_wf_init(const __grid_constant__ nrrt_camera cam, const __grid_constant__ Rende
           const __grid_constant__ WfState W) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w == 0) {
-        W.count[0] = P.n_slots;
-        W.count[1] = 0;
+        W.count[0] = NRRT_SPLIT_QUEUE ? 0 : P.n_slots;  // queue 0: no bounce rays yet ...
+        W.count[1] = NRRT_SPLIT_QUEUE ? P.n_slots : 0;  // ... every slot starts with a camera ray
+        W.count[2] = 0;
+        W.count[3] = 0;
         W.cursor[0] = 0;
         W.cursor[1] = 0;
         W.counters[1] += P.n_slots;
@@ -332,7 +350,7 @@ k_wf_init(const __grid_constant__ nrrt_camera cam, const __grid_constant__ Rende
     W.item[w] = w;
     W.sample[w] = first;
     W.bounce[w] = 0;
-    W.queue[0][w] = w;
+    W.queue[0][NRRT_SPLIT_QUEUE ? n - 1u - w : w] = w;  // camera-ray region: from the back, descending
 }
 
 // traverse / intersect: closest hit for every queued ray.
@@ -347,10 +365,11 @@ __global__ void __launch_bounds__(NRRT_BLOCK, 5)
 k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState W, uint32_t n, uint32_t qin) {
     extern __shared__ uint32_t s_stack[];
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_in = W.count[qin];
+    const uint32_t n_bounce = W.count[2 * qin], n_in = n_bounce + W.count[2 * qin + 1];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        W.count[qin ^ 1] = 0;   // the other queue is filled by the next shade pass
-        W.cursor[qin ^ 1] = 0;  // and consumed by the next extend pass
+        W.count[2 * (qin ^ 1)] = 0;      // the other queue is filled by the next shade pass
+        W.count[2 * (qin ^ 1) + 1] = 0;
+        W.cursor[qin ^ 1] = 0;           // and consumed by the next extend pass
     }
     Traversal<false, false, F> tr;
     bool has = false, exhausted = false;
@@ -366,7 +385,7 @@ k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState 
             if (!has) {
                 uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
                 if (i < n_in) {
-                    slot = W.queue[qin][i];
+                    slot = queue_slot(W.queue[qin], n, n_bounce, i);
                     tr.begin(S, MemCtx{W.ray, W.hit_attr, n, slot}, 0.001, NRRT_INF, nullptr);
                     has = true;
                 }
@@ -395,7 +414,7 @@ k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_came
            const __grid_constant__ RenderParams P, const __grid_constant__ WfState W, uint32_t qin) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n = P.n_slots;
-    const uint32_t n_in = W.count[qin];
+    const uint32_t n_bounce = W.count[2 * qin], n_in = n_bounce + W.count[2 * qin + 1];
     const uint32_t lane_id = threadIdx.x & 31u;
     if (i == 0) W.counters[0] += n_in;  // one closest-hit query per queued ray
     bool active = i < n_in, survive = false, need_item = false, new_path = false;
@@ -404,7 +423,7 @@ k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_came
     Sampler smp{P.key, 0u, 0u};
     WorkItem wi;
     if (active) {
-        slot = W.queue[qin][i];
+        slot = queue_slot(W.queue[qin], n, n_bounce, i);
         o = mk3(W.ray[slot], W.ray[(size_t)n + slot], W.ray[2 * (size_t)n + slot]);
         d = mk3(W.ray[3 * (size_t)n + slot], W.ray[4 * (size_t)n + slot], W.ray[5 * (size_t)n + slot]);
         T = mk3(W.T[slot], W.T[(size_t)n + slot], W.T[2 * (size_t)n + slot]);
@@ -493,13 +512,21 @@ k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_came
         W.T[slot] = T.x, W.T[(size_t)n + slot] = T.y, W.T[2 * (size_t)n + slot] = T.z;
         W.bounce[slot] = bounce;
     }
-    // warp-aggregated compaction of the survivors into the other queue
-    unsigned ballot = __ballot_sync(0xffffffffu, survive);
-    if (ballot) {
-        uint32_t base = 0;
-        if (lane_id == 0) base = atomicAdd(&W.count[qin ^ 1], (uint32_t)__popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (survive) W.queue[qin ^ 1][base + __popc(ballot & ((1u << lane_id) - 1u))] = slot;
+    // warp-aggregated compaction of the survivors into the other queue: bounce rays to the front, freshly generated
+    // camera rays to the back
+    const bool cam_ray = NRRT_SPLIT_QUEUE && survive && new_path;
+    const unsigned b_bounce = __ballot_sync(0xffffffffu, survive && !cam_ray), b_cam = __ballot_sync(0xffffffffu, cam_ray);
+    if (b_bounce | b_cam) {
+        uint32_t base_b = 0, base_c = 0;
+        if (lane_id == 0) {
+            if (b_bounce) base_b = atomicAdd(&W.count[2 * (qin ^ 1)], (uint32_t)__popc(b_bounce));
+            if (b_cam) base_c = atomicAdd(&W.count[2 * (qin ^ 1) + 1], (uint32_t)__popc(b_cam));
+        }
+        base_b = __shfl_sync(0xffffffffu, base_b, 0);
+        base_c = __shfl_sync(0xffffffffu, base_c, 0);
+        const unsigned below = (1u << lane_id) - 1u;
+        if (survive && !cam_ray) W.queue[qin ^ 1][base_b + __popc(b_bounce & below)] = slot;
+        if (cam_ray) W.queue[qin ^ 1][n - 1u - (base_c + __popc(b_cam & below))] = slot;
     }
 }
 
@@ -616,7 +643,7 @@ int nrrt_create(int device, nrrt_ctx** out) {
     }
     if ((e = cudaMalloc((void**)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess)
         return bail("cudaMalloc", e);
-    if ((e = cudaMallocHost((void**)&ctx->h_count, 64 * sizeof(uint32_t))) != cudaSuccess)
+    if ((e = cudaMallocHost((void**)&ctx->h_count, 128 * sizeof(uint32_t))) != cudaSuccess)
         return bail("cudaMallocHost", e);
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -985,7 +1012,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         o_attr = carve(n * 8 * sizeof(double));
         o_q0 = carve(n * sizeof(uint32_t));
         o_q1 = carve(n * sizeof(uint32_t));
-        o_cnt = carve(4 * sizeof(uint32_t));
+        o_cnt = carve(8 * sizeof(uint32_t));
     }
     int rc = ensure_scratch(ctx, std::max<size_t>(off, 256));
     if (rc != NRRT_OK) return rc;
@@ -1026,7 +1053,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         Wf.queue[0] = (uint32_t*)(base + o_q0);
         Wf.queue[1] = (uint32_t*)(base + o_q1);
         Wf.count = (uint32_t*)(base + o_cnt);
-        Wf.cursor = Wf.count + 2;
+        Wf.cursor = Wf.count + 4;
         Wf.partials = d_part;
         Wf.counters = ctx->d_counters;
         k_wf_init<<<work_blocks, NRRT_BLOCK, 0, ctx->stream>>>(c, P, Wf);
@@ -1039,7 +1066,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
             CK(cudaEventCreate(&e));
             ctx->ev_pool.push_back(e);
         }
-        for (int k = 0; k < RING; ++k) ctx->h_count[k] = 0xFFFFFFFFu;
+        for (int k = 0; k < 2 * RING; ++k) ctx->h_count[k] = 0x7FFFFFFFu;
         uint64_t iter = 0, polls_issued = 0, polls_seen = 0;
         // expected iteration count, to spread the timed extend launches over the whole render
         const uint64_t expect_iters = std::max<uint64_t>(1, (uint64_t)P.n_items * P.chunk * 4 / std::max<uint32_t>(P.n_slots, 1u));
@@ -1071,23 +1098,24 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
                 // throttle: never run more than RING polls ahead of the device
                 while (polls_issued - polls_seen >= (uint64_t)RING) {
                     CK(cudaEventSynchronize(ctx->ev_pool[polls_seen % RING]));
-                    if (ctx->h_count[polls_seen % RING] == 0) done = true;
+                    if (ctx->h_count[2 * (polls_seen % RING)] + ctx->h_count[2 * (polls_seen % RING) + 1] == 0) done = true;
                     ++polls_seen;
                 }
                 int slot = (int)(polls_issued % RING);
-                CK(cudaMemcpyAsync(&ctx->h_count[slot], Wf.count + qin, sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                   ctx->stream));
+                CK(cudaMemcpyAsync(&ctx->h_count[2 * slot], Wf.count + 2 * qin, 2 * sizeof(uint32_t),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaEventRecord(ctx->ev_pool[slot], ctx->stream));
                 ++polls_issued;
                 while (polls_seen < polls_issued && cudaEventQuery(ctx->ev_pool[polls_seen % RING]) == cudaSuccess) {
-                    if (ctx->h_count[polls_seen % RING] == 0) done = true;
+                    if (ctx->h_count[2 * (polls_seen % RING)] + ctx->h_count[2 * (polls_seen % RING) + 1] == 0) done = true;
                     ++polls_seen;
                 }
                 // once the queue is nearly drained, wait for each poll instead of launching empty passes
-                if (!done && polls_seen > 0 && ctx->h_count[(polls_seen - 1) % RING] < 4096u) {
+                if (!done && polls_seen > 0 &&
+                    ctx->h_count[2 * ((polls_seen - 1) % RING)] + ctx->h_count[2 * ((polls_seen - 1) % RING) + 1] < 4096u) {
                     while (polls_seen < polls_issued) {
                         CK(cudaEventSynchronize(ctx->ev_pool[polls_seen % RING]));
-                        if (ctx->h_count[polls_seen % RING] == 0) done = true;
+                        if (ctx->h_count[2 * (polls_seen % RING)] + ctx->h_count[2 * (polls_seen % RING) + 1] == 0) done = true;
                         ++polls_seen;
                     }
                 }

@@ -320,11 +320,25 @@ def run_b200(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = (my_segs * bytes_seg) / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else None
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per segment there, scaled to
+        # this run's segments per launch)
+        traffic = issue_pct = lanes = None
+        try:
+            nt = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            k = nt["k_wf_extend" if mode == A.MODE_WAVEFRONT else "k_render_mega"]
+            traffic = k["dram_bytes_per_segment"] * (my_segs / max(ext_launches, 1))
+            issue_pct, lanes = k.get("issue_slot_utilisation_pct"), k.get("active_threads_per_instruction")
+        except (OSError, ValueError, KeyError):
+            pass
         roofline = {
             "bound": "hbm", "kernel": "k_wf_extend" if mode == A.MODE_WAVEFRONT else "k_render_mega",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
             "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650",
-            "traffic": None,
+            "traffic": traffic,
+            "traffic_source": "profiles/ncu_traffic.json (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per "
+                              "segment of the same kernel) x segments per launch of this run",
+            "algorithmic_bytes_per_launch": bytes_seg * (my_segs / max(ext_launches, 1)),
+            "ncu_issue_slot_utilisation_pct": issue_pct, "ncu_active_threads_per_instruction": lanes,
             "bytes_per_segment": bytes_seg, "nodes_per_segment": nodes_seg, "prims_per_segment": prims_seg,
             "exact_box_tests_per_segment": exact_seg, "segments_per_launch": my_segs / max(ext_launches, 1),
             "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": ext_launches,

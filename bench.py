@@ -188,7 +188,8 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    mode = A.MODE_WAVEFRONT if args.mode == "wavefront" else A.MODE_MEGAKERNEL
+    mode = {"fused": A.MODE_FUSED, "wavefront": A.MODE_WAVEFRONT, "megakernel": A.MODE_MEGAKERNEL}[args.mode]
+    kernel_name = {"fused": "k_render_fused", "wavefront": "k_wf_extend", "megakernel": "k_render_mega"}[args.mode]
     R = D.DEFAULT_ROWS_PER_BLOCK
 
     graph = load_scene(SCENE, camera_override=CameraConfig(width=args.width, height=args.height,
@@ -325,13 +326,13 @@ def run_b200(args):
         traffic = issue_pct = lanes = None
         try:
             nt = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            k = nt["k_wf_extend" if mode == A.MODE_WAVEFRONT else "k_render_mega"]
+            k = nt[kernel_name]
             traffic = k["dram_bytes_per_segment"] * (my_segs / max(ext_launches, 1))
             issue_pct, lanes = k.get("issue_slot_utilisation_pct"), k.get("active_threads_per_instruction")
         except (OSError, ValueError, KeyError):
             pass
         roofline = {
-            "bound": "hbm", "kernel": "k_wf_extend" if mode == A.MODE_WAVEFRONT else "k_render_mega",
+            "bound": "hbm", "kernel": kernel_name,
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
             "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650",
             "traffic": traffic,
@@ -363,8 +364,9 @@ def run_b200(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{SCENE} {args.width}x{args.height} {args.spp}spp depth{DEPTH}",
                        "kernel_design": args.mode, "partition": f"row-blocks of {R}, round-robin over {world} GPU(s)",
-                       "l2": "flushed between timed steps (256 MB write); path state (>300 MB) exceeds L2, the scene "
-                             "(KB) is cache-resident by design", "rng": "Philox4x32-10, seed 0"},
+                       "l2": "flushed between timed steps (256 MB write); the scene (KB-MB) is cache-resident by design, path "
+                             "state lives in shared memory (fused) or streams through HBM (wavefront)",
+                       "rng": "Philox4x32-10, seed 0"},
             "time_to_image_s": sum_ms / args.steps / 1e3,
             "segments_per_step": segs / args.steps, "paths_per_step": paths / args.steps,
             "segments_per_path": segs / max(paths, 1),
@@ -390,7 +392,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="wavefront", choices=["wavefront", "megakernel"])
+    ap.add_argument("--mode", default="fused", choices=["fused", "wavefront", "megakernel"])
     ap.add_argument("--scene", default=SCENE, help="scene file (default: the benchmark workload)")
     ap.add_argument("--depth", type=int, default=DEPTH)
     ap.add_argument("--width", type=int, default=WIDTH)

@@ -215,7 +215,7 @@ class Context:
         return {"node_visits": st.node_visits, "box_exact": st.box_exact, "prim_tests": st.prim_tests,
                 "kernel_ms": st.kernel_ms}
 
-    def render(self, cam: A.Camera, out: Optional[np.ndarray] = None, seed: int = 0, mode: int = A.MODE_WAVEFRONT,
+    def render(self, cam: A.Camera, out: Optional[np.ndarray] = None, seed: int = 0, mode: int = A.MODE_FUSED,
                rank: int = 0, world: int = 1, rows_per_block: int = 0, max_slots: int = 0,
                out_device_ptr: Optional[int] = None, progress: Optional[Callable[[int, int], None]] = None,
                count: bool = False):

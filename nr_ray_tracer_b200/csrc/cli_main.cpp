@@ -5,7 +5,7 @@
 //   ->  build  ->  scene.render()  ->  gamma_correction(gamma)  ->  to_rgb8  ->  encode by extension
 // Flags and NR_RT_CAMERA_* environment fallbacks follow ray-tracer/src/cli.rs:113-270 (field of view and defocus
 // angle in degrees; image size needs exactly two of width / height / aspect ratio; default output out.png,
-// default gamma 0.5).  Additions: --seed, --mode wavefront|megakernel, --device N.
+// default gamma 0.5).  Additions: --seed, --mode fused|wavefront|megakernel, --device N.
 // Encoders available without external libraries: .png (stored/uncompressed deflate) and .ppm.
 #include <cerrno>
 #include <chrono>
@@ -119,7 +119,7 @@ static void usage() {
         "      --background-color x,y,z  --look-at x,y,z  --look-from x,y,z  --view-up x,y,z\n"
         "      --field-of-view <DEG>  --defocus-angle <DEG>  --focus-distance <D>\n"
         "      --samples-per-pixel <N>  --ray-max-bounces <N>\n"
-        "      --seed <N>  --mode wavefront|megakernel  --device <N>\n"
+        "      --seed <N>  --mode fused|wavefront|megakernel  --device <N>\n"
         "  -v, --verbose                  print timing\n"
         "Every camera option falls back to NR_RT_CAMERA_<NAME> (e.g. NR_RT_CAMERA_SAMPLES_PER_PIXEL).");
 }
@@ -130,7 +130,7 @@ int main(int argc, char** argv) {
         return argc < 2 ? 2 : 0;
     }
     if (std::strcmp(argv[1], "render") != 0) die(std::string("unknown command '") + argv[1] + "' (only `render` runs on the GPU path)");
-    std::string scene_path, output = "out.png", mode = "wavefront";
+    std::string scene_path, output = "out.png", mode = "fused";
     bool force = false, verbose = false;
     float gamma = 0.5f;  // constants.rs:1
     uint64_t seed = 0;
@@ -240,7 +240,7 @@ int main(int argc, char** argv) {
     std::memset(&opts, 0, sizeof opts);
     opts.seed = seed;
     opts.world = 1;
-    opts.mode = mode == "megakernel" ? NRRT_MODE_MEGAKERNEL : NRRT_MODE_WAVEFRONT;
+    opts.mode = mode == "megakernel" ? NRRT_MODE_MEGAKERNEL : (mode == "wavefront" ? NRRT_MODE_WAVEFRONT : NRRT_MODE_FUSED);
     nrrt_render_stats st;
     auto t0 = std::chrono::steady_clock::now();
     if (nrrt_render(ctx, &cam, &opts, image.data(), nullptr, nullptr, &st) != NRRT_OK) die(nrrt_last_error(ctx));

@@ -289,6 +289,152 @@ __global__ void k_encode_rgb8(const float* __restrict__ rgb, size_t n, float gam
     out[i] = (v == v) ? (uint8_t)q : (uint8_t)0;
 }
 
+// ------------------------------------------------------------------ fused persistent kernel
+// The persistent traverse loop of k_wf_extend, but a lane whose ray is finished does not write a hit record and
+// fetch somebody else's ray: it waits until at least NRRT_FUSED_MIN lanes of its warp are in the same position,
+// then those lanes shade, scatter (or regenerate the next sample / fetch the next work item) and start traversing
+// their own next ray, all together.  Path state lives in shared memory (ray, throughput, running sum, hit
+// attributes: 20 doubles per thread), so neither rays nor hit records ever round-trip through HBM and there is no
+// queue, no compaction and a single launch.  Traversal and shading use the same device functions as the
+// wavefront kernels and the same (pixel, sample-chunk) work items, so the image is bit-identical.
+#ifndef NRRT_FUSED_MIN
+#define NRRT_FUSED_MIN 16
+#endif
+#define NRRT_FUSED_STATE_DOUBLES 20  // o(3) d(3) T(3) sum(3) | attr: p(3) alpha beta dobj(3)
+struct SmemCtx {
+    double* st;  // this thread's column: st[k * NRRT_BLOCK]
+    __device__ __forceinline__ void get(d3& oo, d3& dd) const {
+        oo = mk3(st[0], st[NRRT_BLOCK], st[2 * NRRT_BLOCK]);
+        dd = mk3(st[3 * NRRT_BLOCK], st[4 * NRRT_BLOCK], st[5 * NRRT_BLOCK]);
+    }
+    __device__ __forceinline__ void put(uint32_t level, d3 p, double a, double b, d3 dobj) const {
+        st[12 * NRRT_BLOCK] = p.x, st[13 * NRRT_BLOCK] = p.y, st[14 * NRRT_BLOCK] = p.z;
+        st[15 * NRRT_BLOCK] = a, st[16 * NRRT_BLOCK] = b;
+        if (level) st[17 * NRRT_BLOCK] = dobj.x, st[18 * NRRT_BLOCK] = dobj.y, st[19 * NRRT_BLOCK] = dobj.z;
+    }
+};
+
+// MB = resident blocks per SM the kernel is compiled for (register budget 65536 / (MB * 128)).  Measured on B200:
+// the planes+instances variant spills at 4 blocks (128 regs) and is 11 % faster at 3 blocks (168 regs, spill-free)
+// when shading dominates (Cornell box), but deep-BVH scenes (teapot) and the spill-free sphere variants prefer 4.
+template <uint32_t F, int MB>
+__global__ void __launch_bounds__(NRRT_BLOCK, MB)
+k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_camera cam,
+               const __grid_constant__ RenderParams P, double* __restrict__ partials,
+               unsigned long long* __restrict__ counters) {
+    extern __shared__ uint32_t s_mem[];
+    uint32_t* stack = s_mem + threadIdx.x;
+    double* st = reinterpret_cast<double*>(s_mem + NRRT_STACK_CAP * NRRT_BLOCK) + threadIdx.x;
+    const SmemCtx ctx{st};
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long segs = 0, paths = 0;
+
+    enum : uint32_t { NEED_ITEM = 0, NEED_PATH = 1, TRAVERSING = 2, HIT_READY = 3, RETIRED = 4 };
+    uint32_t state = NEED_ITEM;
+    uint32_t item = w;  // the first n_slots items are pre-assigned; the counter starts at n_slots
+    WorkItem wi;
+    wi.x = wi.y = wi.sample_end = 0;
+    Sampler smp{P.key, 0u, 0u};
+    uint32_t bounce = 0;
+    Traversal<false, false, F> tr;
+
+    for (;;) {
+        // ---- shading / regeneration round, voted by the warp
+        const unsigned pend = __ballot_sync(0xffffffffu, state != TRAVERSING && state != RETIRED);
+        const unsigned trav = __ballot_sync(0xffffffffu, state == TRAVERSING);
+        if (pend == 0 && trav == 0) break;
+        if (pend && (__popc(pend) >= NRRT_FUSED_MIN || trav == 0)) {
+            if (state == HIT_READY) {
+                d3 o, d;
+                ctx.get(o, d);
+                d3 T = mk3(st[6 * NRRT_BLOCK], st[7 * NRRT_BLOCK], st[8 * NRRT_BLOCK]);
+                d3 L = mk3(0.0, 0.0, 0.0);
+                bool alive;
+                const HitId& h = tr.best;
+                if (h.prim == NRRT_REF_NONE) {  // camera.rs:298
+                    L = mul3(T, ld3(cam.background));
+                    alive = false;
+                } else {
+                    HitRec rec;
+                    d3 p_obj = mk3(st[12 * NRRT_BLOCK], st[13 * NRRT_BLOCK], st[14 * NRRT_BLOCK]);
+                    d3 d_dir = d;
+                    if ((F & NRRT_F_INSTANCES) && h.depth)
+                        d_dir = mk3(st[17 * NRRT_BLOCK], st[18 * NRRT_BLOCK], st[19 * NRRT_BLOCK]);
+                    double al = 0.0, be = 0.0;
+                    if (F & NRRT_F_PLANES) al = st[15 * NRRT_BLOCK], be = st[16 * NRRT_BLOCK];
+                    const bool want_uv = (F & NRRT_F_TEXTURED) && (S.material_flags[hit_material<F>(S, h.prim)] & 1u) != 0;
+                    resolve_hit_attr<F>(S, h, p_obj, al, be, d_dir, want_uv, rec);
+                    alive = path_shade<F>(S, cam, rec, smp, o, d, T, L, bounce);
+                }
+                if (alive) {
+                    st[0] = o.x, st[NRRT_BLOCK] = o.y, st[2 * NRRT_BLOCK] = o.z;
+                    st[3 * NRRT_BLOCK] = d.x, st[4 * NRRT_BLOCK] = d.y, st[5 * NRRT_BLOCK] = d.z;
+                    st[6 * NRRT_BLOCK] = T.x, st[7 * NRRT_BLOCK] = T.y, st[8 * NRRT_BLOCK] = T.z;
+                    state = TRAVERSING;
+                } else {  // path finished: add it to the item's partial sum (sample order)
+                    d3 sum = add3(mk3(st[9 * NRRT_BLOCK], st[10 * NRRT_BLOCK], st[11 * NRRT_BLOCK]), L);
+                    ++smp.sample;
+                    if (smp.sample >= wi.sample_end) {  // item finished: publish, fetch the next one
+                        size_t pb = (size_t)item * 3;
+                        partials[pb] = sum.x, partials[pb + 1] = sum.y, partials[pb + 2] = sum.z;
+                        item = (uint32_t)atomicAdd(&counters[5], 1ull);
+                        state = NEED_ITEM;
+                    } else {
+                        st[9 * NRRT_BLOCK] = sum.x, st[10 * NRRT_BLOCK] = sum.y, st[11 * NRRT_BLOCK] = sum.z;
+                        state = NEED_PATH;
+                    }
+                }
+            }
+            if (state == NEED_ITEM) {
+                if (item >= P.n_items) {
+                    state = RETIRED;
+                } else {
+                    smp.sample = decode_item(cam, P, item, wi);
+                    smp.pixel = wi.y * cam.width + wi.x;
+                    st[9 * NRRT_BLOCK] = 0.0, st[10 * NRRT_BLOCK] = 0.0, st[11 * NRRT_BLOCK] = 0.0;
+                    state = NEED_PATH;
+                }
+            }
+            if (state == NEED_PATH) {  // Camera::get_ray for the item's next sample
+                d3 o, d;
+                camera_ray(cam, wi.x, wi.y, smp, o, d);
+                st[0] = o.x, st[NRRT_BLOCK] = o.y, st[2 * NRRT_BLOCK] = o.z;
+                st[3 * NRRT_BLOCK] = d.x, st[4 * NRRT_BLOCK] = d.y, st[5 * NRRT_BLOCK] = d.z;
+                st[6 * NRRT_BLOCK] = 1.0, st[7 * NRRT_BLOCK] = 1.0, st[8 * NRRT_BLOCK] = 1.0;
+                bounce = 0;
+                ++paths;
+                state = TRAVERSING;
+            }
+            // every lane that just became TRAVERSING starts its query (lanes already traversing keep theirs)
+            const bool fresh = (pend >> (threadIdx.x & 31u)) & 1u;
+            if (fresh && state == TRAVERSING) {
+                tr.begin(S, ctx, 0.001, NRRT_INF, nullptr);
+                ++segs;
+            }
+        }
+        // ---- one traversal round for the lanes that have a query
+        if (tr.round(S, ctx, 0.001, NRRT_INF, stack, NRRT_BLOCK, nullptr, state == TRAVERSING) && state == TRAVERSING)
+            state = HIT_READY;
+    }
+    // block-level reduction of the counters
+    __shared__ unsigned long long s_cnt[2];
+    if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = 0;
+    __syncthreads();
+    for (int off = 16; off; off >>= 1) {
+        segs += __shfl_down_sync(0xffffffffu, segs, off);
+        paths += __shfl_down_sync(0xffffffffu, paths, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_cnt[0], segs);
+        atomicAdd(&s_cnt[1], paths);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&counters[0], s_cnt[0]);
+        atomicAdd(&counters[1], s_cnt[1]);
+    }
+}
+
 // ------------------------------------------------------------------ wavefront
 // SoA path state, one entry per slot (n = n_slots).
 struct WfState {
@@ -406,7 +552,7 @@ k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState 
 
 // shade / scatter, in-slot path regeneration, dynamic work fetch, warp-ballot compaction of the survivors
 #ifndef NRRT_SHADE_MINBLOCKS
-#define NRRT_SHADE_MINBLOCKS 5
+#define NRRT_SHADE_MINBLOCKS 6
 #endif
 template <uint32_t F>
 __global__ void __launch_bounds__(NRRT_BLOCK, NRRT_SHADE_MINBLOCKS)
@@ -848,6 +994,32 @@ static void launch_shade(nrrt_ctx* ctx, unsigned blocks, const nrrt_camera& c, c
     }
 }
 
+// blocks per SM for the fused kernel: 3 for small instanced scenes (shading-dominated, see k_render_fused), else 4
+static int fused_blocks_per_sm(const nrrt_ctx* ctx) {
+    return ((ctx->features & NRRT_F_INSTANCES) && ctx->dev.n_nodes < 256) ? 3 : 4;
+}
+static cudaError_t launch_fused(nrrt_ctx* ctx, unsigned blocks, const nrrt_camera& c, const RenderParams& P, double* partials) {
+    const size_t smem = (size_t)NRRT_BLOCK * (NRRT_STACK_CAP * sizeof(uint32_t) + NRRT_FUSED_STATE_DOUBLES * sizeof(double));
+    cudaError_t e = cudaSuccess;
+#define NRRT_FUSED_CASE(FEAT, MB)                                                                                      \
+    e = cudaFuncSetAttribute(k_render_fused<FEAT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    if (e == cudaSuccess)                                                                                              \
+        k_render_fused<FEAT, MB><<<blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, c, P, partials, ctx->d_counters);
+    const bool three = fused_blocks_per_sm(ctx) == 3;
+    switch (ctx->features) {
+        case NRRT_F_CORNELL:
+            if (three) { NRRT_FUSED_CASE(NRRT_F_CORNELL, 3) } else { NRRT_FUSED_CASE(NRRT_F_CORNELL, 4) }
+            break;
+        case NRRT_F_BALLS: NRRT_FUSED_CASE(NRRT_F_BALLS, 4) break;
+        case NRRT_F_BALLS_TEX: NRRT_FUSED_CASE(NRRT_F_BALLS_TEX, 4) break;
+        default:
+            if (three) { NRRT_FUSED_CASE(NRRT_F_ALL, 3) } else { NRRT_FUSED_CASE(NRRT_F_ALL, 4) }
+            break;
+    }
+#undef NRRT_FUSED_CASE
+    return e;
+}
+
 static int ensure_scratch(nrrt_ctx* ctx, size_t bytes) {
     if (ctx->scratch_bytes >= bytes) return NRRT_OK;
     if (ctx->scratch) {
@@ -986,6 +1158,11 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     const bool out_dev = (o.flags & NRRT_RENDER_OUT_DEVICE) != 0;
     const bool counting = (o.flags & NRRT_RENDER_COUNT) != 0;
     const bool wavefront = o.mode == NRRT_MODE_WAVEFRONT && !counting;
+    const bool fused = o.mode == NRRT_MODE_FUSED && !counting;
+    if (fused) {  // persistent: one thread per resident lane; the work counter hands out the rest
+        const uint64_t resident = (uint64_t)(ctx->persistent_blocks / 5) * fused_blocks_per_sm(ctx) * NRRT_BLOCK;
+        P.n_slots = (uint32_t)std::min<uint64_t>(n_items64, o.max_slots ? std::min<uint64_t>(o.max_slots, resident) : resident);
+    }
     const size_t fb_bytes = (size_t)total_pixels * 3 * sizeof(float);
     const size_t n = P.n_slots;
     // scratch layout
@@ -1031,6 +1208,10 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     if (n == 0 || c.ray_max_bounces == 0) {
         // nothing owned, or every path returns black at depth 0 (camera.rs:276-278)
         if (P.n_items) CK(cudaMemsetAsync(d_part, 0, (size_t)P.n_items * 3 * sizeof(double), ctx->stream));
+    } else if (fused) {
+        CK(launch_fused(ctx, work_blocks, c, P, d_part));
+        CK(cudaGetLastError());
+        ++launches;
     } else if (!wavefront) {
         if (counting)
             k_render_mega<true><<<work_blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, c, P, d_part, ctx->d_counters);

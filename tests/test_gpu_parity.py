@@ -18,7 +18,7 @@ from tests.scenes_util import ALL_SCENES, BASELINE_SCENES, load
 
 pytestmark = pytest.mark.gpu
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
-MODES = [(A.MODE_WAVEFRONT, "wavefront"), (A.MODE_MEGAKERNEL, "megakernel")]
+MODES = [(A.MODE_WAVEFRONT, "wavefront"), (A.MODE_MEGAKERNEL, "megakernel"), (A.MODE_FUSED, "fused")]
 
 
 def _scene(ctx, g):
@@ -152,8 +152,8 @@ def test_render_same_streams_matches_oracle(gpu_ctx, name):
         assert abs(st["segments"] - cnt["segments"]) <= 0.005 * cnt["segments"] + 2
         assert abs(float(img.mean()) - float(ref.mean())) <= 0.01 * float(ref.mean()) + 1e-6
         imgs.append(img)
-    # the two kernels designs share device functions and streams: identical images
-    assert np.array_equal(imgs[0], imgs[1])
+    # the kernel designs share device functions, work items and streams: identical images
+    assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])
     del hs
 
 
@@ -257,7 +257,9 @@ def test_full_size_properties_1080p(gpu_ctx):
     b, sb = gpu_ctx.render(cam, seed=1, mode=A.MODE_WAVEFRONT)
     c, sc = gpu_ctx.render(cam, seed=1, mode=A.MODE_MEGAKERNEL)
     d, _ = gpu_ctx.render(cam, seed=2, mode=A.MODE_WAVEFRONT)
-    assert np.array_equal(a, b) and np.array_equal(a, c) and not np.array_equal(a, d)
+    e, se = gpu_ctx.render(cam, seed=1, mode=A.MODE_FUSED)
+    assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, e) and not np.array_equal(a, d)
+    assert se["segments"] == sa["segments"] and se["paths"] == sa["paths"]
     assert sa["paths"] == 1920 * 1080 * 2 == sc["paths"] and sa["segments"] == sb["segments"] == sc["segments"]
     assert np.isfinite(a).all() and (a >= 0).all()
     # the 64 top-left pixels against the oracle

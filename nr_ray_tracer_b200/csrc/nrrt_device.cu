@@ -300,9 +300,19 @@ __global__ void k_encode_rgb8(const float* __restrict__ rgb, size_t n, float gam
 #ifndef NRRT_FUSED_MIN
 #define NRRT_FUSED_MIN 16
 #endif
-#define NRRT_FUSED_STATE_DOUBLES 20  // o(3) d(3) T(3) sum(3) | attr: p(3) alpha beta dobj(3)
+#define NRRT_FUSED_STATE_DOUBLES 26  // o(3) d(3) T(3) sum(3) | attr: p(3) alpha beta dobj(3) | object-space ray (6)
+#define NRRT_FUSED_STATE_WORDS 4     // item, pixel x, pixel y, sample_end (touched only between paths)
 struct SmemCtx {
+    static constexpr bool kRayInCtx = true;
     double* st;  // this thread's column: st[k * NRRT_BLOCK]
+    __device__ __forceinline__ void get_obj(d3& oo, d3& dd) const {
+        oo = mk3(st[20 * NRRT_BLOCK], st[21 * NRRT_BLOCK], st[22 * NRRT_BLOCK]);
+        dd = mk3(st[23 * NRRT_BLOCK], st[24 * NRRT_BLOCK], st[25 * NRRT_BLOCK]);
+    }
+    __device__ __forceinline__ void put_obj(d3 oo, d3 dd) const {
+        st[20 * NRRT_BLOCK] = oo.x, st[21 * NRRT_BLOCK] = oo.y, st[22 * NRRT_BLOCK] = oo.z;
+        st[23 * NRRT_BLOCK] = dd.x, st[24 * NRRT_BLOCK] = dd.y, st[25 * NRRT_BLOCK] = dd.z;
+    }
     __device__ __forceinline__ void get(d3& oo, d3& dd) const {
         oo = mk3(st[0], st[NRRT_BLOCK], st[2 * NRRT_BLOCK]);
         dd = mk3(st[3 * NRRT_BLOCK], st[4 * NRRT_BLOCK], st[5 * NRRT_BLOCK]);
@@ -314,9 +324,8 @@ struct SmemCtx {
     }
 };
 
-// MB = resident blocks per SM the kernel is compiled for (register budget 65536 / (MB * 128)).  Measured on B200:
-// the planes+instances variant spills at 4 blocks (128 regs) and is 11 % faster at 3 blocks (168 regs, spill-free)
-// when shading dominates (Cornell box), but deep-BVH scenes (teapot) and the spill-free sphere variants prefer 4.
+// MB = resident blocks per SM the kernel is compiled for (register budget 65536 / (MB * 128)).  Measured on B200
+// (Cornell / spheres / teapot, Mseg/s): 3 blocks 4440 / 2957 / 791, 4 blocks 4770 / 3495 / 940.
 template <uint32_t F, int MB>
 __global__ void __launch_bounds__(NRRT_BLOCK, MB)
 k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_camera cam,
@@ -326,14 +335,20 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
     uint32_t* stack = s_mem + threadIdx.x;
     double* st = reinterpret_cast<double*>(s_mem + NRRT_STACK_CAP * NRRT_BLOCK) + threadIdx.x;
     const SmemCtx ctx{st};
+    // per-path bookkeeping that is only touched between paths lives in shared memory too
+    uint32_t* wd = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(s_mem + NRRT_STACK_CAP * NRRT_BLOCK) +
+                                               NRRT_FUSED_STATE_DOUBLES * NRRT_BLOCK) + threadIdx.x;
+    uint32_t& s_item = wd[0];
+    uint32_t& s_px = wd[NRRT_BLOCK];
+    uint32_t& s_py = wd[2 * NRRT_BLOCK];
+    uint32_t& s_end = wd[3 * NRRT_BLOCK];
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long segs = 0, paths = 0;
+    uint32_t segs = 0, paths = 0;  // per-thread; a thread traces far fewer than 2^32 segments
 
     enum : uint32_t { NEED_ITEM = 0, NEED_PATH = 1, TRAVERSING = 2, HIT_READY = 3, RETIRED = 4 };
     uint32_t state = NEED_ITEM;
-    uint32_t item = w;  // the first n_slots items are pre-assigned; the counter starts at n_slots
-    WorkItem wi;
-    wi.x = wi.y = wi.sample_end = 0;
+    s_item = w;  // the first n_slots items are pre-assigned; the counter starts at n_slots
+    s_px = s_py = s_end = 0;
     Sampler smp{P.key, 0u, 0u};
     uint32_t bounce = 0;
     Traversal<false, false, F> tr;
@@ -374,10 +389,10 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
                 } else {  // path finished: add it to the item's partial sum (sample order)
                     d3 sum = add3(mk3(st[9 * NRRT_BLOCK], st[10 * NRRT_BLOCK], st[11 * NRRT_BLOCK]), L);
                     ++smp.sample;
-                    if (smp.sample >= wi.sample_end) {  // item finished: publish, fetch the next one
-                        size_t pb = (size_t)item * 3;
+                    if (smp.sample >= s_end) {  // item finished: publish, fetch the next one
+                        size_t pb = (size_t)s_item * 3;
                         partials[pb] = sum.x, partials[pb + 1] = sum.y, partials[pb + 2] = sum.z;
-                        item = (uint32_t)atomicAdd(&counters[5], 1ull);
+                        s_item = (uint32_t)atomicAdd(&counters[5], 1ull);
                         state = NEED_ITEM;
                     } else {
                         st[9 * NRRT_BLOCK] = sum.x, st[10 * NRRT_BLOCK] = sum.y, st[11 * NRRT_BLOCK] = sum.z;
@@ -386,18 +401,20 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
                 }
             }
             if (state == NEED_ITEM) {
-                if (item >= P.n_items) {
+                if (s_item >= P.n_items) {
                     state = RETIRED;
                 } else {
-                    smp.sample = decode_item(cam, P, item, wi);
+                    WorkItem wi;
+                    smp.sample = decode_item(cam, P, s_item, wi);
                     smp.pixel = wi.y * cam.width + wi.x;
+                    s_px = wi.x, s_py = wi.y, s_end = wi.sample_end;
                     st[9 * NRRT_BLOCK] = 0.0, st[10 * NRRT_BLOCK] = 0.0, st[11 * NRRT_BLOCK] = 0.0;
                     state = NEED_PATH;
                 }
             }
             if (state == NEED_PATH) {  // Camera::get_ray for the item's next sample
                 d3 o, d;
-                camera_ray(cam, wi.x, wi.y, smp, o, d);
+                camera_ray(cam, s_px, s_py, smp, o, d);
                 st[0] = o.x, st[NRRT_BLOCK] = o.y, st[2 * NRRT_BLOCK] = o.z;
                 st[3 * NRRT_BLOCK] = d.x, st[4 * NRRT_BLOCK] = d.y, st[5 * NRRT_BLOCK] = d.z;
                 st[6 * NRRT_BLOCK] = 1.0, st[7 * NRRT_BLOCK] = 1.0, st[8 * NRRT_BLOCK] = 1.0;
@@ -420,13 +437,14 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
     __shared__ unsigned long long s_cnt[2];
     if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = 0;
     __syncthreads();
+    unsigned long long segs64 = segs, paths64 = paths;
     for (int off = 16; off; off >>= 1) {
-        segs += __shfl_down_sync(0xffffffffu, segs, off);
-        paths += __shfl_down_sync(0xffffffffu, paths, off);
+        segs64 += __shfl_down_sync(0xffffffffu, segs64, off);
+        paths64 += __shfl_down_sync(0xffffffffu, paths64, off);
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&s_cnt[0], segs);
-        atomicAdd(&s_cnt[1], paths);
+        atomicAdd(&s_cnt[0], segs64);
+        atomicAdd(&s_cnt[1], paths64);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -994,12 +1012,18 @@ static void launch_shade(nrrt_ctx* ctx, unsigned blocks, const nrrt_camera& c, c
     }
 }
 
-// blocks per SM for the fused kernel: 3 for small instanced scenes (shading-dominated, see k_render_fused), else 4
+// blocks per SM for the fused kernel
 static int fused_blocks_per_sm(const nrrt_ctx* ctx) {
-    return ((ctx->features & NRRT_F_INSTANCES) && ctx->dev.n_nodes < 256) ? 3 : 4;
+    if (const char* e = std::getenv("NRRT_FUSED_BLOCKS")) {  // developer override for occupancy experiments
+        int v = std::atoi(e);
+        if (v == 3 || v == 4) return v;
+    }
+    (void)ctx;
+    return 4;  // measured: with path bookkeeping and the current-space ray in shared memory, 4 wins on every scene
 }
 static cudaError_t launch_fused(nrrt_ctx* ctx, unsigned blocks, const nrrt_camera& c, const RenderParams& P, double* partials) {
-    const size_t smem = (size_t)NRRT_BLOCK * (NRRT_STACK_CAP * sizeof(uint32_t) + NRRT_FUSED_STATE_DOUBLES * sizeof(double));
+    const size_t smem = (size_t)NRRT_BLOCK * (NRRT_STACK_CAP * sizeof(uint32_t) + NRRT_FUSED_STATE_DOUBLES * sizeof(double) +
+                                              NRRT_FUSED_STATE_WORDS * sizeof(uint32_t));
     cudaError_t e = cudaSuccess;
 #define NRRT_FUSED_CASE(FEAT, MB)                                                                                      \
     e = cudaFuncSetAttribute(k_render_fused<FEAT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \

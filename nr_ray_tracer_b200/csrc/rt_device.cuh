@@ -319,9 +319,14 @@ __device__ __forceinline__ bool root_box_test(const nrrt_box* b, const Ray32& r3
 //   get(): the world-space ray (needed again when an instance is left)
 //   put(): attributes of a candidate that just became the best hit
 // Fixed-ray queries / megakernel: ray in registers, attributes recomputed later by resolve_hit.
+// kRayInCtx: the context also keeps the CURRENT-space ray (world at level 0, object space inside an instance), so
+// the traversal state does not pin 12 registers for it across the node loop (fused kernel: shared memory).
 struct RegCtx {
+    static constexpr bool kRayInCtx = false;
     d3 o, d;
     __device__ __forceinline__ void get(d3& oo, d3& dd) const { oo = o, dd = d; }
+    __device__ __forceinline__ void get_obj(d3&, d3&) const {}
+    __device__ __forceinline__ void put_obj(d3, d3) const {}
     __device__ __forceinline__ void put(uint32_t, d3, double, double, d3) const {}
 };
 // Wavefront: ray re-read from the SoA path state (saves 12 registers across the node loop); attributes go straight
@@ -329,6 +334,9 @@ struct RegCtx {
 // alpha/beta.  attr = [8][n]: object-space hit point xyz, alpha, beta, and (hits inside an instance only) the
 // object-space ray direction xyz that decides front_face.
 struct MemCtx {
+    static constexpr bool kRayInCtx = false;
+    __device__ __forceinline__ void get_obj(d3&, d3&) const {}
+    __device__ __forceinline__ void put_obj(d3, d3) const {}
     const double* ray;  // [6][n]
     double* attr;       // [8][n]
     uint32_t n, slot;
@@ -366,6 +374,25 @@ struct Traversal {
     uint32_t cur_inst[NRRT_MAX_INSTANCE_DEPTH];
     HitId best;
 
+    // the ray in the current space: from the traversal state, or from the context when it owns it
+    template <class Ctx>
+    __device__ __forceinline__ void load_ray(const Ctx& ctx, d3& oo, d3& dd) const {
+        if (Ctx::kRayInCtx) {
+            if (!(F & NRRT_F_INSTANCES) || level == 0) ctx.get(oo, dd);
+            else ctx.get_obj(oo, dd);
+        } else {
+            oo = o, dd = d;
+        }
+    }
+    template <class Ctx>
+    __device__ __forceinline__ void store_ray(const Ctx& ctx, d3 oo, d3 dd) {  // call AFTER `level` is updated
+        if (Ctx::kRayInCtx) {
+            if ((F & NRRT_F_INSTANCES) && level > 0) ctx.put_obj(oo, dd);
+        } else {
+            o = oo, d = dd;
+        }
+    }
+
     // filter bounds of the query range; the margins cover the rounding
     static __device__ __forceinline__ float lo32(double tmin) { return (float)tmin; }
     static __device__ __forceinline__ float hi32(double tmax) { return (tmax < 3.0e38) ? (float)tmax : 3.4e38f; }
@@ -380,14 +407,16 @@ struct Traversal {
 #pragma unroll
         for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) best.inst[k] = 0, cur_inst[k] = 0;
         level = 0;
-        ctx.get(o, d);
-        r32 = make_ray32(o, d);
+        d3 wo, wd;
+        ctx.get(wo, wd);
+        store_ray(ctx, wo, wd);
+        r32 = make_ray32(wo, wd);
         tcull = 3.4e38f;                                    // f32 upper bound of best.t (+ slack)
         sp = 0;
         cur = S.root;
         // root of the scene: an inner node tests its own box (object.rs:102)
         if (NRRT_REF_TYPE(cur) == NRRT_REF_NODE &&
-            !root_box_test<COUNT>(&S.root_box, r32, o, d, tmin, tmax, tmin32, tmax32, cnt))
+            !root_box_test<COUNT>(&S.root_box, r32, wo, wd, tmin, tmax, tmin32, tmax32, cnt))
             cur = NRRT_REF_NONE;
     }
 
@@ -414,6 +443,8 @@ struct Traversal {
             bool amb0 = v0 && NRRT_REF_TYPE(c0) == NRRT_REF_NODE && (r32.degenerate || !(g0 >= m0));
             bool amb1 = v1 && NRRT_REF_TYPE(c1) == NRRT_REF_NODE && (r32.degenerate || !(g1 >= m1));
             if (amb0 || amb1) {  // rare
+                d3 o, d;
+                load_ray(ctx, o, d);
                 if (amb0) {
                     if (COUNT) cnt->exact++;
                     v0 = box_hit_exact(S.child_boxes + 2 * (size_t)ni, o, d, tmin, tmax);
@@ -457,6 +488,8 @@ struct Traversal {
 #endif
         }
         if (!has) return true;
+        d3 o, d;
+        if (is_prim || is_inst) load_ray(ctx, o, d);
         if (is_prim) {
             if (serve_inst) return false;  // wait: this round enters instances
             if (COUNT) cnt->prims++;
@@ -505,7 +538,7 @@ struct Traversal {
                     ++sp;
                     cur_inst[level] = ii;
                     ++level;
-                    o = no, d = nd;
+                    store_ray(ctx, no, nd);
                     r32 = n32;
                     cur = inner;
                     return false;
@@ -528,9 +561,11 @@ struct Traversal {
             in_hand = false;
             if (!(F & NRRT_F_INSTANCES) || cur != NRRT_REF_POP) return false;
             --level;
-            ctx.get(o, d);
-            for (uint32_t l = 0; l < level; ++l) instance_ray(S, cur_inst[l], o, d);
-            r32 = make_ray32(o, d);
+            d3 po, pd;
+            ctx.get(po, pd);
+            for (uint32_t l = 0; l < level; ++l) instance_ray(S, cur_inst[l], po, pd);
+            store_ray(ctx, po, pd);
+            r32 = make_ray32(po, pd);
         }
     }
 };

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NRRT_ABI_VERSION 2
+#define NRRT_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------ */
 enum {
@@ -52,7 +52,8 @@ enum {
 /* ======================================================================== */
 
 enum nrrt_obj_kind {
-    NRRT_OBJ_SPHERE = 0,    /* v[0..2]=center v[3]=radius       objects/sphere.rs:69-91   */
+    NRRT_OBJ_SPHERE = 0,    /* v[0..2]=center v[3]=radius v[4..6]=speed (SphereBuilder::with_speed, zero = none:
+                             * center(t) = center + t*speed, t = Ray::time in [0,1))  objects/sphere.rs:45-51,69-91 */
     NRRT_OBJ_QUAD = 1,      /* v[0..2]=p v[3..5]=u v[6..8]=v    objects/plane.rs:95-127   */
     NRRT_OBJ_TRIANGLE = 2,  /* same as quad, Shape::Triangle                              */
     NRRT_OBJ_GROUP = 3,     /* BVH::from(children)  (Group, Scene, and the scene list)    */
@@ -248,6 +249,10 @@ typedef struct nrrt_scene_desc {
     const nrrt_image* images;
 
     uint32_t max_stack; /* worst-case traversal stack entries (validated by the host) */
+
+    /* moving spheres (sphere.rs:110-111): speed vector per sphere, or NULL when no sphere moves (every shipped
+     * scene); kept out of sphere_rec so static scenes keep the 32-byte record */
+    const double* sphere_speed; /* [n][3] or NULL */
 } nrrt_scene_desc;
 
 #define NRRT_PLANE_TRIANGLE_BIT 0x80000000u
@@ -339,6 +344,9 @@ typedef struct nrrt_trace_stats {
     uint64_t prim_tests;    /*   exact primitive tests                               */
     double kernel_ms;       /* CUDA-event time of the kernel (always)                */
 } nrrt_trace_stats;
+
+/* Ray::time (ray.rs:8) of the rays given to nrrt_trace_rays, default 0.  Only moving spheres read it. */
+int nrrt_set_trace_time(nrrt_ctx* ctx, double time);
 
 /* BVH::hit (object.rs:89-121) for n rays: rays = n x {ox,oy,oz,dx,dy,dz}. */
 int nrrt_trace_rays(nrrt_ctx* ctx, const double* rays, uint64_t n, double tmin, double tmax,

@@ -5,7 +5,7 @@ struct sizes against the values the compiled library reports.
 """
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # status codes
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NO_SCENE, ERR_LIMIT, ERR_IO = 0, -1, -2, -3, -4, -5, -6
@@ -100,6 +100,7 @@ class SceneDesc(C.Structure):
         ("n_textures", u32), ("textures", C.POINTER(Texture)),
         ("n_images", u32), ("images", C.POINTER(Image)),
         ("max_stack", u32),
+        ("sphere_speed", C.POINTER(f64)),
     ]
 
 

@@ -60,6 +60,7 @@ def lib() -> C.CDLL:
         L.nrrt_last_error.restype = C.c_char_p
         L.nrrt_last_error.argtypes = [C.c_void_p]
         L.nrrt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.nrrt_set_trace_time.argtypes = [C.c_void_p, C.c_double]
         L.nrrt_scene_upload.argtypes = [C.c_void_p, C.POINTER(A.SceneDesc)]
         L.nrrt_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_uint32,
                                       C.c_void_p, C.POINTER(A.TraceStats)]
@@ -189,6 +190,10 @@ class Context:
 
     def set_stream(self, cuda_stream: int):
         self._check(lib().nrrt_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_trace_time(self, time: float):
+        """Ray::time of the rays given to trace_rays (ray.rs:8); only moving spheres read it."""
+        self._check(lib().nrrt_set_trace_time(self._h, float(time)))
 
     def upload(self, scene: HostScene):
         self._check(lib().nrrt_scene_upload(self._h, C.byref(scene.desc)))

@@ -64,6 +64,8 @@ struct Flattener {
     std::vector<nrrt_node> nodes;
     std::vector<nrrt_box> child_boxes;
     std::vector<double> sphere_rec;  // 4 doubles per sphere
+    std::vector<double> sphere_speed;  // 3 doubles per sphere
+    bool any_motion = false;
     std::vector<uint32_t> sphere_material, sphere_order, sphere_object;
     std::vector<double> plane_rec;   // 16 doubles per plane
     std::vector<uint32_t> plane_material, plane_order, plane_object;
@@ -101,7 +103,7 @@ struct Flattener {
                 if (o.material >= g.n_materials) fail("material index out of range");
                 D3 c{o.v[0], o.v[1], o.v[2]};
                 D3 r{o.v[3], o.v[3], o.v[3]};
-                D3 c1 = c + D3{0, 0, 0};  // center + speed.unwrap_or(ZERO)
+                D3 c1 = c + D3{o.v[4], o.v[5], o.v[6]};  // center + speed.unwrap_or(ZERO), sphere.rs:75-76
                 Aabb b0 = Aabb::from_points(c - r, c + r);
                 Aabb b1 = Aabb::from_points(c1 - r, c1 + r);
                 in.box = b0.unite(b1);
@@ -234,6 +236,10 @@ struct Flattener {
             case NRRT_OBJ_SPHERE: {
                 uint32_t idx = (uint32_t)sphere_material.size();
                 for (int k = 0; k < 4; ++k) sphere_rec.push_back(o.v[k]);
+                for (int k = 4; k < 7; ++k) {
+                    sphere_speed.push_back(o.v[k]);
+                    if (o.v[k] != 0.0) any_motion = true;  // Some(ZERO) behaves exactly like None
+                }
                 sphere_material.push_back(o.material);
                 sphere_order.push_back(sp.order++);
                 sphere_object.push_back(oi);
@@ -476,6 +482,7 @@ nrrt_host_scene* nrrt_host_build(const nrrt_graph_desc* g) {
         d.n_images = (uint32_t)hs->images.size();
         d.images = hs->images.data();
         d.max_stack = root.depth + 2;
+        d.sphere_speed = f.any_motion ? f.sphere_speed.data() : nullptr;
         return hs.release();
     } catch (const HostError& e) {
         g_error = e.msg;

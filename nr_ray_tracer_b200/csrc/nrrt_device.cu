@@ -101,7 +101,7 @@ __device__ __forceinline__ uint32_t decode_item(const nrrt_camera& cam, const Re
 template <bool VISIT_ALL, bool COUNT>
 __global__ void __launch_bounds__(NRRT_BLOCK)
 k_trace_rays(const __grid_constant__ DevScene S, const double* __restrict__ rays, uint64_t n, double tmin, double tmax,
-             nrrt_hit* __restrict__ out, unsigned long long* __restrict__ counters) {
+             double time, nrrt_hit* __restrict__ out, unsigned long long* __restrict__ counters) {
     extern __shared__ uint32_t s_stack[];
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;  // no early return: trace_closest votes across the whole warp
@@ -109,7 +109,7 @@ k_trace_rays(const __grid_constant__ DevScene S, const double* __restrict__ rays
     if (valid) o = ld3(rays + 6 * i), d = ld3(rays + 6 * i + 3);
     HitId h;
     TraceCounters tc{0, 0, 0, 0, 0};
-    trace_closest<VISIT_ALL, COUNT>(S, o, d, tmin, tmax, s_stack + threadIdx.x, NRRT_BLOCK, h, &tc, valid);
+    trace_closest<VISIT_ALL, COUNT>(S, o, d, time, tmin, tmax, s_stack + threadIdx.x, NRRT_BLOCK, h, &tc, valid);
     if (!valid) return;
     nrrt_hit r;
     r.t = h.t;
@@ -120,7 +120,7 @@ k_trace_rays(const __grid_constant__ DevScene S, const double* __restrict__ rays
     r._pad = 0;
     if (h.prim != NRRT_REF_NONE) {
         HitRec rec;
-        resolve_hit(S, h, o, d, true, rec);
+        resolve_hit(S, h, o, d, time, true, rec);
         r.point[0] = rec.point.x, r.point[1] = rec.point.y, r.point[2] = rec.point.z;
         r.normal[0] = rec.normal.x, r.normal[1] = rec.normal.y, r.normal[2] = rec.normal.z;
         r.uv[0] = rec.u, r.uv[1] = rec.v;
@@ -166,13 +166,13 @@ __device__ __forceinline__ bool path_shade(const DevScene& S, const nrrt_camera&
     return bounce < cam.ray_max_bounces;  // camera.rs:276-278
 }
 __device__ __forceinline__ bool path_step(const DevScene& S, const nrrt_camera& cam, const HitId& h, const Sampler& smp,
-                                          d3& o, d3& d, d3& T, d3& L, uint32_t& bounce) {
+                                          d3& o, d3& d, double time, d3& T, d3& L, uint32_t& bounce) {
     if (h.prim == NRRT_REF_NONE) {  // camera.rs:298
         L = add3(L, mul3(T, ld3(cam.background)));
         return false;
     }
     HitRec rec;
-    resolve_hit(S, h, o, d, (S.material_flags[hit_material(S, h.prim)] & 1u) != 0, rec);
+    resolve_hit(S, h, o, d, time, (S.material_flags[hit_material(S, h.prim)] & 1u) != 0, rec);
     return path_shade(S, cam, rec, smp, o, d, T, L, bounce);
 }
 
@@ -194,6 +194,7 @@ k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
         Sampler smp{P.key, 0u, 0u};
         d3 sum = mk3(0.0, 0.0, 0.0);
         d3 o = mk3(0.0, 0.0, 0.0), d = o, T = o, L = o;
+        double time = 0.0;
         uint32_t bounce = 0;
         bool alive = false, have_item = false;
         bool running = w < P.n_slots;
@@ -210,7 +211,7 @@ k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
                     }
                 }
                 if (running) {
-                    camera_ray(cam, wi.x, wi.y, smp, o, d);
+                    camera_ray<true>(cam, wi.x, wi.y, smp, o, d, time);
                     T = mk3(1.0, 1.0, 1.0);
                     L = mk3(0.0, 0.0, 0.0);
                     bounce = 0;
@@ -219,10 +220,10 @@ k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
                 }
             }
             HitId h;
-            trace_closest<false, COUNT>(S, o, d, 0.001, NRRT_INF, s_stack + threadIdx.x, NRRT_BLOCK, h, &tc, running);
+            trace_closest<false, COUNT>(S, o, d, time, 0.001, NRRT_INF, s_stack + threadIdx.x, NRRT_BLOCK, h, &tc, running);
             if (running) {
                 ++segs;
-                alive = path_step(S, cam, h, smp, o, d, T, L, bounce);
+                alive = path_step(S, cam, h, smp, o, d, time, T, L, bounce);
                 if (!alive) {
                     sum = add3(sum, L);
                     if (++smp.sample >= wi.sample_end) {  // chunk done: publish its partial sum, fetch the next item
@@ -300,11 +301,13 @@ __global__ void k_encode_rgb8(const float* __restrict__ rgb, size_t n, float gam
 #ifndef NRRT_FUSED_MIN
 #define NRRT_FUSED_MIN 16
 #endif
-#define NRRT_FUSED_STATE_DOUBLES 26  // o(3) d(3) T(3) sum(3) | attr: p(3) alpha beta dobj(3) | object-space ray (6)
+#define NRRT_FUSED_STATE_DOUBLES 27  // o(3) d(3) T(3) sum(3) | attr: p(3) alpha beta dobj(3) | object-space ray (6) | time
+#define NRRT_FUSED_BLOCKS_PER_SM 4   // resident blocks the kernel is compiled for (measured: 4 beats 3 on every scene)
 #define NRRT_FUSED_STATE_WORDS 4     // item, pixel x, pixel y, sample_end (touched only between paths)
 struct SmemCtx {
     static constexpr bool kRayInCtx = true;
     double* st;  // this thread's column: st[k * NRRT_BLOCK]
+    __device__ __forceinline__ double time() const { return st[26 * NRRT_BLOCK]; }
     __device__ __forceinline__ void get_obj(d3& oo, d3& dd) const {
         oo = mk3(st[20 * NRRT_BLOCK], st[21 * NRRT_BLOCK], st[22 * NRRT_BLOCK]);
         dd = mk3(st[23 * NRRT_BLOCK], st[24 * NRRT_BLOCK], st[25 * NRRT_BLOCK]);
@@ -378,7 +381,7 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
                     double al = 0.0, be = 0.0;
                     if (F & NRRT_F_PLANES) al = st[15 * NRRT_BLOCK], be = st[16 * NRRT_BLOCK];
                     const bool want_uv = (F & NRRT_F_TEXTURED) && (S.material_flags[hit_material<F>(S, h.prim)] & 1u) != 0;
-                    resolve_hit_attr<F>(S, h, p_obj, al, be, d_dir, want_uv, rec);
+                    resolve_hit_attr<F>(S, h, p_obj, al, be, d_dir, (F & NRRT_F_MOTION) ? ctx.time() : 0.0, want_uv, rec);
                     alive = path_shade<F>(S, cam, rec, smp, o, d, T, L, bounce);
                 }
                 if (alive) {
@@ -414,7 +417,9 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
             }
             if (state == NEED_PATH) {  // Camera::get_ray for the item's next sample
                 d3 o, d;
-                camera_ray(cam, s_px, s_py, smp, o, d);
+                double tm;
+                camera_ray<(F & NRRT_F_MOTION) != 0>(cam, s_px, s_py, smp, o, d, tm);
+                if (F & NRRT_F_MOTION) st[26 * NRRT_BLOCK] = tm;
                 st[0] = o.x, st[NRRT_BLOCK] = o.y, st[2 * NRRT_BLOCK] = o.z;
                 st[3 * NRRT_BLOCK] = d.x, st[4 * NRRT_BLOCK] = d.y, st[5 * NRRT_BLOCK] = d.z;
                 st[6 * NRRT_BLOCK] = 1.0, st[7 * NRRT_BLOCK] = 1.0, st[8 * NRRT_BLOCK] = 1.0;
@@ -456,7 +461,7 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
 // ------------------------------------------------------------------ wavefront
 // SoA path state, one entry per slot (n = n_slots).
 struct WfState {
-    double* ray;       // [6][n]: ox oy oz dx dy dz
+    double* ray;       // [7][n]: ox oy oz dx dy dz time
     double* T;         // [3][n] throughput.  (The radiance of a LIVE path is identically zero: no reference
                        //        material both emits and scatters — material.rs:10-27, diffuse_light.rs — so it
                        //        is not stored; a path contributes T*background or T*emitted when it ends.)
@@ -504,7 +509,9 @@ k_wf_init(const __grid_constant__ nrrt_camera cam, const __grid_constant__ Rende
     uint32_t first = decode_item(cam, P, w, wi);
     Sampler smp{P.key, wi.y * cam.width + wi.x, first};
     d3 o, d;
-    camera_ray(cam, wi.x, wi.y, smp, o, d);
+    double tm;
+    camera_ray<true>(cam, wi.x, wi.y, smp, o, d, tm);
+    W.ray[6 * (size_t)n + w] = tm;
     W.ray[0 * (size_t)n + w] = o.x, W.ray[1 * (size_t)n + w] = o.y, W.ray[2 * (size_t)n + w] = o.z;
     W.ray[3 * (size_t)n + w] = d.x, W.ray[4 * (size_t)n + w] = d.y, W.ray[5 * (size_t)n + w] = d.z;
     for (int c = 0; c < 3; ++c) {
@@ -609,7 +616,7 @@ k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_came
                 h.inst[l] = ((F & NRRT_F_INSTANCES) && l < h.depth) ? W.hit_inst[(size_t)l * n + slot] : 0u;
         }
 #if !NRRT_HIT_SINK
-        survive = path_step(S, cam, h, smp, o, d, T, L, bounce);
+        survive = path_step(S, cam, h, smp, o, d, W.ray[6 * (size_t)n + slot], T, L, bounce);
 #else
         if (h.prim == NRRT_REF_NONE) {  // camera.rs:298
             L = mul3(T, ld3(cam.background));
@@ -624,7 +631,8 @@ k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_came
             double al = 0.0, be = 0.0;
             if (F & NRRT_F_PLANES) al = A[3 * (size_t)n + slot], be = A[4 * (size_t)n + slot];
             const bool want_uv = (F & NRRT_F_TEXTURED) && (S.material_flags[hit_material<F>(S, h.prim)] & 1u) != 0;
-            resolve_hit_attr<F>(S, h, p_obj, al, be, d_dir, want_uv, rec);
+            resolve_hit_attr<F>(S, h, p_obj, al, be, d_dir, (F & NRRT_F_MOTION) ? W.ray[6 * (size_t)n + slot] : 0.0, want_uv,
+                                rec);
             survive = path_shade<F>(S, cam, rec, smp, o, d, T, L, bounce);
         }
 #endif
@@ -660,7 +668,9 @@ k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_came
     if (active && !survive) {
         W.sum[slot] = sum.x, W.sum[(size_t)n + slot] = sum.y, W.sum[2 * (size_t)n + slot] = sum.z;
         if (new_path) {  // regenerate in place: next sample of the item
-            camera_ray(cam, wi.x, wi.y, smp, o, d);
+            double tm;
+            camera_ray<(F & NRRT_F_MOTION) != 0>(cam, wi.x, wi.y, smp, o, d, tm);
+            if (F & NRRT_F_MOTION) W.ray[6 * (size_t)n + slot] = tm;
             T = mk3(1.0, 1.0, 1.0);
             L = mk3(0.0, 0.0, 0.0);
             bounce = 0;
@@ -716,6 +726,7 @@ struct nrrt_ctx {
     std::vector<cudaEvent_t> ev_pool;
     unsigned persistent_blocks = 592;  // SMs x resident blocks of the extend kernel
     uint32_t features = NRRT_F_ALL;    // NRRT_F_* mask of the uploaded scene
+    double trace_time = 0.0;           // Ray::time of nrrt_trace_rays queries
 };
 
 #define CK(call)                                                                                   \
@@ -837,6 +848,12 @@ int nrrt_set_stream(nrrt_ctx* ctx, void* cuda_stream) {
     return NRRT_OK;
 }
 
+int nrrt_set_trace_time(nrrt_ctx* ctx, double time) {
+    if (!ctx) return NRRT_ERR_INVALID;
+    ctx->trace_time = time;
+    return NRRT_OK;
+}
+
 static uint32_t pick_features(uint32_t need);
 
 int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
@@ -869,6 +886,11 @@ int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
     D.root = sc->root;
     D.root_box = sc->root_box;
     UP(sphere_rec, sc->sphere_rec, (size_t)sc->n_spheres * 4);
+    if (sc->n_spheres && sc->sphere_speed) {
+        UP(sphere_speed, sc->sphere_speed, (size_t)sc->n_spheres * 3);
+    } else {
+        D.sphere_speed = nullptr;
+    }
     UP(sphere_material, sc->sphere_material, sc->n_spheres);
     UP(sphere_order, sc->sphere_order, sc->n_spheres);
     UP(sphere_object, sc->sphere_object, sc->n_spheres);
@@ -976,6 +998,7 @@ int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
             if (sc->textures[i].kind != NRRT_TEX_SOLID) need |= NRRT_F_TEXTURED;
         for (uint32_t i = 0; i < sc->n_materials; ++i)
             if (sc->materials[i].kind == NRRT_MAT_DIELECTRIC) need |= NRRT_F_DIELECTRIC;
+        if (sc->n_spheres && sc->sphere_speed) need |= NRRT_F_MOTION;
         ctx->features = pick_features(need);
     }
     ctx->dev = D;
@@ -989,8 +1012,9 @@ int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
 #define NRRT_F_CORNELL (NRRT_F_PLANES | NRRT_F_INSTANCES)                 // planar scenes with wrappers, solid colours
 #define NRRT_F_BALLS (NRRT_F_SPHERES | NRRT_F_DIELECTRIC)                  // sphere fields, solid colours
 #define NRRT_F_BALLS_TEX (NRRT_F_SPHERES | NRRT_F_TEXTURED)                // textured spheres (earth, noise)
+#define NRRT_F_GENERAL (NRRT_F_ALL & ~NRRT_F_MOTION)                       // everything a scene file can describe
 static uint32_t pick_features(uint32_t need) {
-    for (uint32_t cand : {NRRT_F_CORNELL, NRRT_F_BALLS, NRRT_F_BALLS_TEX})
+    for (uint32_t cand : {NRRT_F_CORNELL, NRRT_F_BALLS, NRRT_F_BALLS_TEX, NRRT_F_GENERAL})
         if ((need & ~cand) == 0) return cand;
     return NRRT_F_ALL;
 }
@@ -999,6 +1023,7 @@ static void launch_extend(nrrt_ctx* ctx, unsigned blocks, size_t smem, const WfS
         case NRRT_F_CORNELL: k_wf_extend<NRRT_F_CORNELL><<<blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, Wf, n, qin); break;
         case NRRT_F_BALLS: k_wf_extend<NRRT_F_BALLS><<<blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, Wf, n, qin); break;
         case NRRT_F_BALLS_TEX: k_wf_extend<NRRT_F_BALLS_TEX><<<blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, Wf, n, qin); break;
+        case NRRT_F_GENERAL: k_wf_extend<NRRT_F_GENERAL><<<blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, Wf, n, qin); break;
         default: k_wf_extend<NRRT_F_ALL><<<blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, Wf, n, qin); break;
     }
 }
@@ -1008,19 +1033,11 @@ static void launch_shade(nrrt_ctx* ctx, unsigned blocks, const nrrt_camera& c, c
         case NRRT_F_CORNELL: k_wf_shade<NRRT_F_CORNELL><<<blocks, NRRT_BLOCK, 0, ctx->stream>>>(ctx->dev, c, P, Wf, qin); break;
         case NRRT_F_BALLS: k_wf_shade<NRRT_F_BALLS><<<blocks, NRRT_BLOCK, 0, ctx->stream>>>(ctx->dev, c, P, Wf, qin); break;
         case NRRT_F_BALLS_TEX: k_wf_shade<NRRT_F_BALLS_TEX><<<blocks, NRRT_BLOCK, 0, ctx->stream>>>(ctx->dev, c, P, Wf, qin); break;
+        case NRRT_F_GENERAL: k_wf_shade<NRRT_F_GENERAL><<<blocks, NRRT_BLOCK, 0, ctx->stream>>>(ctx->dev, c, P, Wf, qin); break;
         default: k_wf_shade<NRRT_F_ALL><<<blocks, NRRT_BLOCK, 0, ctx->stream>>>(ctx->dev, c, P, Wf, qin); break;
     }
 }
 
-// blocks per SM for the fused kernel
-static int fused_blocks_per_sm(const nrrt_ctx* ctx) {
-    if (const char* e = std::getenv("NRRT_FUSED_BLOCKS")) {  // developer override for occupancy experiments
-        int v = std::atoi(e);
-        if (v == 3 || v == 4) return v;
-    }
-    (void)ctx;
-    return 4;  // measured: with path bookkeeping and the current-space ray in shared memory, 4 wins on every scene
-}
 static cudaError_t launch_fused(nrrt_ctx* ctx, unsigned blocks, const nrrt_camera& c, const RenderParams& P, double* partials) {
     const size_t smem = (size_t)NRRT_BLOCK * (NRRT_STACK_CAP * sizeof(uint32_t) + NRRT_FUSED_STATE_DOUBLES * sizeof(double) +
                                               NRRT_FUSED_STATE_WORDS * sizeof(uint32_t));
@@ -1029,16 +1046,12 @@ static cudaError_t launch_fused(nrrt_ctx* ctx, unsigned blocks, const nrrt_camer
     e = cudaFuncSetAttribute(k_render_fused<FEAT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
     if (e == cudaSuccess)                                                                                              \
         k_render_fused<FEAT, MB><<<blocks, NRRT_BLOCK, smem, ctx->stream>>>(ctx->dev, c, P, partials, ctx->d_counters);
-    const bool three = fused_blocks_per_sm(ctx) == 3;
     switch (ctx->features) {
-        case NRRT_F_CORNELL:
-            if (three) { NRRT_FUSED_CASE(NRRT_F_CORNELL, 3) } else { NRRT_FUSED_CASE(NRRT_F_CORNELL, 4) }
-            break;
-        case NRRT_F_BALLS: NRRT_FUSED_CASE(NRRT_F_BALLS, 4) break;
-        case NRRT_F_BALLS_TEX: NRRT_FUSED_CASE(NRRT_F_BALLS_TEX, 4) break;
-        default:
-            if (three) { NRRT_FUSED_CASE(NRRT_F_ALL, 3) } else { NRRT_FUSED_CASE(NRRT_F_ALL, 4) }
-            break;
+        case NRRT_F_CORNELL: NRRT_FUSED_CASE(NRRT_F_CORNELL, NRRT_FUSED_BLOCKS_PER_SM) break;
+        case NRRT_F_BALLS: NRRT_FUSED_CASE(NRRT_F_BALLS, NRRT_FUSED_BLOCKS_PER_SM) break;
+        case NRRT_F_BALLS_TEX: NRRT_FUSED_CASE(NRRT_F_BALLS_TEX, NRRT_FUSED_BLOCKS_PER_SM) break;
+        case NRRT_F_GENERAL: NRRT_FUSED_CASE(NRRT_F_GENERAL, NRRT_FUSED_BLOCKS_PER_SM) break;
+        default: NRRT_FUSED_CASE(NRRT_F_ALL, NRRT_FUSED_BLOCKS_PER_SM) break;
     }
 #undef NRRT_FUSED_CASE
     return e;
@@ -1088,14 +1101,14 @@ int nrrt_trace_rays(nrrt_ctx* ctx, const double* rays, uint64_t n, double tmin, 
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (flags & NRRT_TRACE_VISIT_ALL) {
         if (count)
-            k_trace_rays<true, true><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, d_out, ctx->d_counters);
+            k_trace_rays<true, true><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, ctx->trace_time, d_out, ctx->d_counters);
         else
-            k_trace_rays<true, false><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, d_out, ctx->d_counters);
+            k_trace_rays<true, false><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, ctx->trace_time, d_out, ctx->d_counters);
     } else {
         if (count)
-            k_trace_rays<false, true><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, d_out, ctx->d_counters);
+            k_trace_rays<false, true><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, ctx->trace_time, d_out, ctx->d_counters);
         else
-            k_trace_rays<false, false><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, d_out, ctx->d_counters);
+            k_trace_rays<false, false><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, ctx->trace_time, d_out, ctx->d_counters);
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -1184,7 +1197,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     const bool wavefront = o.mode == NRRT_MODE_WAVEFRONT && !counting;
     const bool fused = o.mode == NRRT_MODE_FUSED && !counting;
     if (fused) {  // persistent: one thread per resident lane; the work counter hands out the rest
-        const uint64_t resident = (uint64_t)(ctx->persistent_blocks / 5) * fused_blocks_per_sm(ctx) * NRRT_BLOCK;
+        const uint64_t resident = (uint64_t)(ctx->persistent_blocks / 5) * NRRT_FUSED_BLOCKS_PER_SM * NRRT_BLOCK;
         P.n_slots = (uint32_t)std::min<uint64_t>(n_items64, o.max_slots ? std::min<uint64_t>(o.max_slots, resident) : resident);
     }
     const size_t fb_bytes = (size_t)total_pixels * 3 * sizeof(float);
@@ -1201,7 +1214,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     size_t o_ray = 0, o_T = 0, o_sum = 0, o_attr = 0, o_item = 0, o_sample = 0, o_bounce = 0, o_ht = 0, o_hp = 0, o_hi = 0,
            o_q0 = 0, o_q1 = 0, o_cnt = 0;
     if (wavefront) {
-        o_ray = carve(n * 6 * sizeof(double));
+        o_ray = carve(n * 7 * sizeof(double));
         o_T = carve(n * 3 * sizeof(double));
         o_sum = carve(n * 3 * sizeof(double));
         o_item = carve(n * sizeof(uint32_t));

@@ -30,7 +30,8 @@
 #define NRRT_F_INSTANCES 4u
 #define NRRT_F_TEXTURED 8u      // any non-solid texture (checker / image / noise / marble)
 #define NRRT_F_DIELECTRIC 16u
-#define NRRT_F_ALL 31u
+#define NRRT_F_MOTION 32u       // moving spheres (SphereBuilder::with_speed): rays carry Ray::time
+#define NRRT_F_ALL 63u
 #define NRRT_STACK_CAP 32          // traversal stack entries per thread (host validates max_stack)
 #define NRRT_REF_POP 0xC0000000u   // type 6: "leave instance level" marker on the stack
 #define NRRT_INF __longlong_as_double(0x7ff0000000000000LL)
@@ -42,6 +43,7 @@ struct DevScene {
     uint32_t root;
     nrrt_box root_box;
     const double* sphere_rec;  // [n][4]: center xyz, radius
+    const double* sphere_speed;  // [n][3] or nullptr when no sphere moves
     const uint32_t* sphere_material;
     const uint32_t* sphere_order;
     const uint32_t* sphere_object;
@@ -178,11 +180,21 @@ __device__ __noinline__ bool box_hit_exact(const nrrt_box* b, d3 o, d3 d, double
 }
 
 // --------------------------------------------------------------------------- primitives
+// center(t) = Ray::new(center, speed.unwrap_or(ZERO)).at(time) (sphere.rs:110-111); compiled only into kernels that
+// handle NRRT_F_MOTION, and a no-op for scenes without moving spheres.
+template <uint32_t F>
+__device__ __forceinline__ d3 sphere_center(const DevScene& S, uint32_t i, d3 c, double time) {
+    if ((F & NRRT_F_MOTION) && S.sphere_speed != nullptr) c = add3(c, scale3(ld3(S.sphere_speed + 3 * (size_t)i), time));
+    return c;
+}
+
 // Sphere::hit (objects/sphere.rs:105-147): returns t or NaN for a miss.
-__device__ __forceinline__ double sphere_t(const DevScene& S, uint32_t i, d3 o, d3 d, double tmin, double tmax) {
+template <uint32_t F = NRRT_F_ALL>
+__device__ __forceinline__ double sphere_t(const DevScene& S, uint32_t i, d3 o, d3 d, double tmin, double tmax,
+                                           double time) {
     const double2* rec = reinterpret_cast<const double2*>(S.sphere_rec) + 2 * (size_t)i;
     double2 r0 = __ldg(rec), r1 = __ldg(rec + 1);
-    d3 c = mk3(r0.x, r0.y, r1.x);
+    d3 c = sphere_center<F>(S, i, mk3(r0.x, r0.y, r1.x), time);
     double r = r1.y;
     d3 ec = sub3(c, o);
     double a = dot3(d, d);
@@ -324,6 +336,8 @@ __device__ __forceinline__ bool root_box_test(const nrrt_box* b, const Ray32& r3
 struct RegCtx {
     static constexpr bool kRayInCtx = false;
     d3 o, d;
+    double tm;  // Ray::time
+    __device__ __forceinline__ double time() const { return tm; }
     __device__ __forceinline__ void get(d3& oo, d3& dd) const { oo = o, dd = d; }
     __device__ __forceinline__ void get_obj(d3&, d3&) const {}
     __device__ __forceinline__ void put_obj(d3, d3) const {}
@@ -337,9 +351,10 @@ struct MemCtx {
     static constexpr bool kRayInCtx = false;
     __device__ __forceinline__ void get_obj(d3&, d3&) const {}
     __device__ __forceinline__ void put_obj(d3, d3) const {}
-    const double* ray;  // [6][n]
+    const double* ray;  // [7][n]: origin, direction, time
     double* attr;       // [8][n]
     uint32_t n, slot;
+    __device__ __forceinline__ double time() const { return ray[6 * (size_t)n + slot]; }
     __device__ __forceinline__ void get(d3& oo, d3& dd) const {
         oo = mk3(ray[slot], ray[(size_t)n + slot], ray[2 * (size_t)n + slot]);
         dd = mk3(ray[3 * (size_t)n + slot], ray[4 * (size_t)n + slot], ray[5 * (size_t)n + slot]);
@@ -497,7 +512,7 @@ struct Traversal {
             d3 pt;
             double t;
             if ((F & NRRT_F_SPHERES) && (!(F & NRRT_F_PLANES) || ty == NRRT_REF_SPHERE)) {
-                t = sphere_t(S, NRRT_REF_INDEX(cur), o, d, tmin, tmax);
+                t = sphere_t<F>(S, NRRT_REF_INDEX(cur), o, d, tmin, tmax, (F & NRRT_F_MOTION) ? ctx.time() : 0.0);
                 pt = ray_at(o, d, t);
             } else {
                 t = plane_t(S, NRRT_REF_INDEX(cur), o, d, tmin, tmax, VISIT_ALL ? NRRT_INF : best.t, &a_, &b_, &pt);
@@ -573,11 +588,11 @@ struct Traversal {
 // Convenience: run one query per lane to completion (fixed-ray queries, megakernel).  Must be called by all 32
 // lanes of the warp; lanes with active = false only take part in the votes.
 template <bool VISIT_ALL, bool COUNT>
-__device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, double tmin, double tmax,
+__device__ __forceinline__ void trace_closest(const DevScene& S, d3 wo, d3 wd, double time, double tmin, double tmax,
                                               uint32_t* stack, uint32_t sstride, HitId& best, TraceCounters* cnt,
                                               bool active) {
     Traversal<VISIT_ALL, COUNT> tr;
-    const RegCtx ctx{wo, wd};
+    const RegCtx ctx{wo, wd, time};
     if (active) tr.begin(S, ctx, tmin, tmax, cnt);
     bool running = active;
     while (__any_sync(0xffffffffu, running)) {
@@ -596,7 +611,7 @@ struct HitRec {
 
 // Rebuilds HitRecord (hitable.rs:38-59) of the winning primitive: object-space point/normal/uv from the
 // object-space ray, then back out through the wrappers.  want_uv=false skips the sphere's acos/atan2.
-__device__ __forceinline__ void resolve_hit(const DevScene& S, const HitId& h, d3 wo, d3 wd, bool want_uv,
+__device__ __forceinline__ void resolve_hit(const DevScene& S, const HitId& h, d3 wo, d3 wd, double time, bool want_uv,
                                             HitRec& rec) {
     d3 o = wo, d = wd;
     for (uint32_t l = 0; l < h.depth; ++l) instance_ray(S, h.inst[l], o, d);
@@ -604,7 +619,7 @@ __device__ __forceinline__ void resolve_hit(const DevScene& S, const HitId& h, d
     d3 point = ray_at(o, d, h.t), outward;
     double u = 0.0, v = 0.0;
     if (ty == NRRT_REF_SPHERE) {
-        d3 c = ld3(S.sphere_rec + 4 * (size_t)ix);
+        d3 c = sphere_center<NRRT_F_ALL>(S, ix, ld3(S.sphere_rec + 4 * (size_t)ix), time);
         outward = normalize3(sub3(point, c));  // sphere.rs:151
         if (want_uv) {                         // sphere.rs:153-159
             const double PI = 3.14159265358979323846264338327950288;
@@ -638,12 +653,12 @@ __device__ __forceinline__ void resolve_hit(const DevScene& S, const HitId& h, d
 // primitive's space (the world direction for depth 0).
 template <uint32_t F = NRRT_F_ALL>
 __device__ __forceinline__ void resolve_hit_attr(const DevScene& S, const HitId& h, d3 p_obj, double alpha, double beta,
-                                                 d3 d_dir, bool want_uv, HitRec& rec) {
+                                                 d3 d_dir, double time, bool want_uv, HitRec& rec) {
     uint32_t ty = NRRT_REF_TYPE(h.prim), ix = NRRT_REF_INDEX(h.prim);
     d3 point = p_obj, outward;
     double u = alpha, v = beta;
     if ((F & NRRT_F_SPHERES) && (!(F & NRRT_F_PLANES) || ty == NRRT_REF_SPHERE)) {
-        d3 c = ld3(S.sphere_rec + 4 * (size_t)ix);
+        d3 c = sphere_center<F>(S, ix, ld3(S.sphere_rec + 4 * (size_t)ix), time);
         outward = normalize3(sub3(point, c));  // sphere.rs:151
         u = 0.0, v = 0.0;
         if ((F & NRRT_F_TEXTURED) && want_uv) {  // sphere.rs:153-159
@@ -896,13 +911,19 @@ __device__ __forceinline__ bool shade_hit(const DevScene& S, const HitRec& h, d3
 
 // --------------------------------------------------------------------------- camera
 // Camera::get_ray (camera.rs:244-267)
+// MOTION: also return Ray::time = random_range(0.0..1.0) (:264) — the third word of the jitter draw.
+template <bool MOTION>
 __device__ __forceinline__ void camera_ray(const nrrt_camera& cam, uint32_t x, uint32_t y, const Sampler& s, d3& o,
-                                           d3& d) {
+                                           d3& d, double& time) {
     double ox = 0.0, oy = 0.0;
-    if (cam.samples_per_pixel > 1) {
+    time = 0.0;
+    if (MOTION || cam.samples_per_pixel > 1) {
         uint4 r = s.draw(0, 0);
-        ox = u_mh_h(r.x);
-        oy = u_mh_h(r.y);
+        if (cam.samples_per_pixel > 1) {
+            ox = u_mh_h(r.x);
+            oy = u_mh_h(r.y);
+        }
+        if (MOTION) time = u_0_1(r.z);
     }
     d3 point = add3(add3(ld3(cam.viewport_top_left), scale3(ld3(cam.pixel_delta_u), xadd((double)x, ox))),
                     scale3(ld3(cam.pixel_delta_v), xadd((double)y, oy)));

@@ -292,14 +292,15 @@ using HitPtr = std::shared_ptr<Hitable>;
 
 // ----------------------------------------------------- objects/sphere.rs
 struct Sphere : Hitable {
-    V3 center;
+    V3 center, speed;  // speed: Option<DVec3>; None and Some(ZERO) are numerically the same (:76, :110)
     double radius;
     const Material* material;
     AABB box;
     uint32_t object;
-    Sphere(V3 c, double r, const Material* m, uint32_t obj) : center(c), radius(r), material(m), object(obj) {
+    Sphere(V3 c, V3 spd, double r, const Material* m, uint32_t obj)
+        : center(c), speed(spd), radius(r), material(m), object(obj) {
         V3 rvec = v3(r, r, r);  // :72
-        V3 c0 = center, c1 = center + v3(0, 0, 0);  // speed = None -> ZERO (:76)
+        V3 c0 = center, c1 = center + speed;  // :75-76
         AABB b0 = AABB::from_points(c0 - rvec, c0 + rvec);
         AABB b1 = AABB::from_points(c1 - rvec, c1 + rvec);
         box = b0.unite(b1);
@@ -307,7 +308,7 @@ struct Sphere : Hitable {
     AABB bbox() const override { return box; }
     OptHit hit(const Ray& ray, Interval range, Counters& cn) const override {  // :105-163
         cn.prim_tests++;
-        V3 ctr = center + ray.time * v3(0, 0, 0);  // Ray::new(center, ZERO).at(time)
+        V3 ctr = center + ray.time * speed;  // Ray::new(center, speed).at(time) (:110-111, ray.rs at())
         V3 dir = ray.direction, eye = ray.origin;
         V3 ec = ctr - eye;
         double a = length_squared(dir);
@@ -851,7 +852,7 @@ static HitPtr build_object(Scene& sc, const nrrt_graph_desc& g, uint32_t idx, in
         case NRRT_OBJ_SPHERE: {
             const Material* m = mat();
             if (!m) return nullptr;
-            out = std::make_shared<Sphere>(v3(o.v[0], o.v[1], o.v[2]), o.v[3], m, idx);
+            out = std::make_shared<Sphere>(v3(o.v[0], o.v[1], o.v[2]), v3(o.v[4], o.v[5], o.v[6]), o.v[3], m, idx);
             break;
         }
         case NRRT_OBJ_QUAD:
@@ -1014,8 +1015,11 @@ static Ray get_ray(const nrrt_camera& cam, uint32_t x, uint32_t y, const Sampler
         V3 p = random_in_unit_disk(s);
         origin = ld3(cam.look_from) + p.x * ddu + p.y * ddv;
     }
-    // time = random_range(0.0..1.0) (:264) only feeds moving spheres, which no scene file can create
-    return Ray{origin, point - origin, 0, 0.0};
+    // time = random_range(0.0..1.0) (:264): third word of the stage-0 / iteration-0 draw.  It only feeds moving
+    // spheres (SphereBuilder::with_speed), which no scene file can create but the library API can.
+    uint32_t rt[4];
+    s.draw(0, 0, rt);
+    return Ray{origin, point - origin, 0, u_0_1(rt[2])};
 }
 
 static V3 get_ray_color(const nrrt_camera& cam, const Scene& sc, const Ray& ray, size_t bounce, const Sampler& s,
@@ -1065,7 +1069,11 @@ int oracle_camera_build(const nrrt_camera_config* cfg, nrrt_camera* out) {
     return 0;
 }
 
-// BVH::hit for n rays (bounce flag 0, time 0).  counters: [aabb_tests, prim_tests]
+// Ray::time of the fixed-ray queries below (default 0): lets the tests probe moving spheres at any shutter time.
+static double g_trace_time = 0.0;
+void oracle_set_trace_time(double t) { g_trace_time = t; }
+
+// BVH::hit for n rays (bounce flag 0, time = oracle_set_trace_time).  counters: [aabb_tests, prim_tests]
 int oracle_trace_rays(const oracle_scene* s, const double* rays, uint64_t n, double tmin, double tmax, nrrt_hit* out,
                       uint64_t* counters, int n_threads) {
     if (!s || !rays || !out) return -1;
@@ -1076,7 +1084,7 @@ int oracle_trace_rays(const oracle_scene* s, const double* rays, uint64_t n, dou
 #pragma omp parallel for schedule(dynamic, 1024) reduction(+ : aabb, prim)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         Counters c;
-        Ray r{ld3(rays + 6 * i), ld3(rays + 6 * i + 3), 0, 0.0};
+        Ray r{ld3(rays + 6 * i), ld3(rays + 6 * i + 3), 0, g_trace_time};
         OptHit h = s->sc->root->hit(r, Interval{tmin, tmax}, c);
         nrrt_hit& o = out[i];
         std::memset(&o, 0, sizeof o);

@@ -37,6 +37,7 @@ def lib() -> C.CDLL:
         L.oracle_camera_build.argtypes = [C.POINTER(A.CameraConfig), C.POINTER(A.Camera)]
         L.oracle_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_void_p,
                                         C.c_void_p, C.c_int]
+        L.oracle_set_trace_time.argtypes = [C.c_double]
         L.oracle_render.argtypes = [C.c_void_p, C.POINTER(A.Camera), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                     C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_texture_eval.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -88,10 +89,12 @@ class OracleScene:
         except Exception:
             pass
 
-    def trace_rays(self, rays: np.ndarray, tmin: float = 0.001, tmax: float = float("inf"), n_threads: int = 0):
+    def trace_rays(self, rays: np.ndarray, tmin: float = 0.001, tmax: float = float("inf"), n_threads: int = 0,
+                   time: float = 0.0):
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
         out = np.zeros(rays.shape[0], dtype=A.HIT_DTYPE)
         counters = np.zeros(2, dtype=np.uint64)
+        lib().oracle_set_trace_time(float(time))
         rc = lib().oracle_trace_rays(self._h, rays.ctypes.data, rays.shape[0], tmin, tmax, out.ctypes.data,
                                      counters.ctypes.data, n_threads)
         if rc != 0:

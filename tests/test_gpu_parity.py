@@ -329,3 +329,79 @@ def test_errors_are_reported_not_swallowed(gpu_ctx):
     with pytest.raises(api.NrrtError):
         api.Context(9999)
     ctx.close()
+
+
+def _moving_scene(with_planes: bool):
+    """Spheres with SphereBuilder::with_speed (sphere.rs:45-51) — unreachable from scene files, reachable from the API."""
+    from nr_ray_tracer_b200.scene_config import CameraConfig, SceneGraph
+    g = SceneGraph()
+    rng = np.random.default_rng(5)
+    t = g.add_texture(kind=A.TEX_SOLID, color=(0.7, 0.6, 0.5))
+    ck = g.add_texture(kind=A.TEX_CHECKER, a=t, b=g.add_texture(kind=A.TEX_SOLID, color=(0.1, 0.2, 0.3)), f0=0.7)
+    mats = [g.add_material(A.MAT_LAMBERTIAN, t), g.add_material(A.MAT_METAL, t, 0.2),
+            g.add_material(A.MAT_DIELECTRIC, 0, 1.5), g.add_material(A.MAT_LAMBERTIAN, ck)]
+    kids = []
+    for i in range(40):
+        c = rng.uniform(-4, 4, 3)
+        sp = rng.uniform(-1.5, 1.5, 3) if i % 3 else np.zeros(3)   # a third of them static
+        kids.append(g.add_object(A.OBJ_SPHERE, mats[i % 4], v=(*c, rng.uniform(0.2, 0.7), *sp)))
+    if with_planes:
+        kids.append(g.add_object(A.OBJ_QUAD, mats[0], v=(-6, -5, -6, 12, 0, 0, 0, 0, 12)))
+        inner = g.add_object(A.OBJ_GROUP, children=[g.add_object(A.OBJ_SPHERE, mats[1], v=(0, 0, 0, 0.5, 0.8, 0.1, 0)),
+                                                    g.add_object(A.OBJ_TRIANGLE, mats[0], v=(0, 0, 1, 1, 0, 0, 0, 1, 0))])
+        kids.append(g.add_object(A.OBJ_TRANSLATE, children=[g.add_object(A.OBJ_ROTATE_Y, children=[inner], v=(0.4,))],
+                                 v=(0, 3, 0)))
+    g.root = g.add_object(A.OBJ_GROUP, children=kids)
+    g.camera = CameraConfig(width=96, height=54, samples_per_pixel=8, ray_max_bounces=8, look_from=(0.0, 1.0, 12.0),
+                            look_at=(0.0, 0.0, 0.0), background_color=(0.5, 0.7, 1.0), field_of_view=50.0)
+    return g
+
+
+@pytest.mark.parametrize("with_planes", [False, True])
+def test_moving_spheres_match_oracle(gpu_ctx, with_planes):
+    """sphere.rs:110-111 (center(t) = center + time*speed), camera.rs:264 (time per camera ray)."""
+    g = _moving_scene(with_planes)
+    hs = _scene(gpu_ctx, g)
+    assert bool(hs.desc.sphere_speed)
+    osc = O.OracleScene(g)
+    rays = np.concatenate([kat.aimed_rays(g, 40000), kat.random_rays(g, 40000)])
+    try:
+        for tm in (0.0, 0.37, 0.999):
+            ref, _ = osc.trace_rays(rays, time=tm)
+            gpu_ctx.set_trace_time(tm)
+            for visit_all in (False, True):
+                gpu, _ = gpu_ctx.trace_rays(rays, visit_all=visit_all)
+                res = kat.compare_hits(gpu, ref)
+                assert kat.hits_ok(res) and res["hits"] > 3000, (tm, res)
+    finally:
+        gpu_ctx.set_trace_time(0.0)
+    # hits at different shutter times differ (the test has teeth)
+    a, _ = osc.trace_rays(rays, time=0.0)
+    b, _ = osc.trace_rays(rays, time=0.999)
+    assert (a["t"] != b["t"]).mean() > 0.01
+    cam = api.camera_build(g.camera.to_builder_config())
+    ref, cnt = osc.render(O.camera_build(g.camera.to_builder_config()), seed=11)
+    imgs = []
+    for mode, mname in MODES:
+        img, st = gpu_ctx.render(cam, seed=11, mode=mode)
+        rel = np.abs(img.astype(np.float64) - ref) / np.maximum(1e-3, np.abs(ref))
+        assert float((rel <= 1e-5).all(axis=2).mean()) >= 0.99, mname
+        assert abs(st["segments"] - cnt["segments"]) <= 0.005 * cnt["segments"] + 2
+        imgs.append(img)
+    assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])
+    del hs
+
+
+def test_zero_speed_is_identical_to_static(gpu_ctx):
+    from nr_ray_tracer_b200.scene_config import SceneGraph
+    imgs = []
+    for speed in ((), (0.0, 0.0, 0.0)):
+        g = load("spheres.toml", width=96, height=54, samples_per_pixel=4)
+        g.objects = [(k, m, c, v[:4] + tuple(speed) + v[4 + len(speed):]) if k == A.OBJ_SPHERE else (k, m, c, v)
+                     for (k, m, c, v) in g.objects]
+        hs = _scene(gpu_ctx, g)
+        assert not bool(hs.desc.sphere_speed)
+        img, _ = gpu_ctx.render(api.camera_build(g.camera.to_builder_config()), seed=5)
+        imgs.append(img)
+        del hs
+    assert np.array_equal(imgs[0], imgs[1])

@@ -169,3 +169,29 @@ def test_shared_group_behind_two_instances_is_flattened_once():
         assert (h is None) == (ref["object"][i] == 0xFFFFFFFF)
         if h is not None:
             assert h[1] == ref["object"][i] and h[0] == ref["t"][i]
+
+
+def test_moving_sphere_bbox_is_union_of_both_shutter_ends_and_speed_is_exported():
+    """sphere.rs:72-78: bbox = union(box at center, box at center + speed); static scenes export no speed array."""
+    from nr_ray_tracer_b200 import api
+    from nr_ray_tracer_b200.scene_config import SceneGraph
+    g = SceneGraph()
+    t = g.add_texture(kind=A.TEX_SOLID, color=(1, 1, 1))
+    m = g.add_material(A.MAT_LAMBERTIAN, t)
+    a = g.add_object(A.OBJ_SPHERE, m, v=(0, 0, 0, 1, 3, -2, 0.5))
+    b = g.add_object(A.OBJ_SPHERE, m, v=(10, 0, 0, 1))
+    g.root = g.add_object(A.OBJ_GROUP, children=[a, b])
+    hs = api.HostScene(g)
+    d = hs.desc
+    assert d.abi_version == A.ABI_VERSION and d.n_spheres == 2 and bool(d.sphere_speed)
+    speed = np.ctypeslib.as_array(d.sphere_speed, shape=(2, 3))
+    obj = np.ctypeslib.as_array(d.sphere_object, shape=(2,))
+    assert speed[list(obj).index(a)].tolist() == [3.0, -2.0, 0.5] and speed[list(obj).index(b)].tolist() == [0, 0, 0]
+    assert list(d.root_box.lo) == [-1.0, -3.0, -1.0] and list(d.root_box.hi) == [11.0, 1.0, 1.5]
+    # a scene whose spheres all have zero speed exports no speed array -> static kernels
+    g2 = SceneGraph()
+    t2 = g2.add_texture(kind=A.TEX_SOLID, color=(1, 1, 1))
+    m2 = g2.add_material(A.MAT_LAMBERTIAN, t2)
+    g2.root = g2.add_object(A.OBJ_GROUP, children=[g2.add_object(A.OBJ_SPHERE, m2, v=(0, 0, 0, 1, 0, 0, 0)),
+                                                   g2.add_object(A.OBJ_SPHERE, m2, v=(3, 0, 0, 1))])
+    assert not bool(api.HostScene(g2).desc.sphere_speed)

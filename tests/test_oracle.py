@@ -274,3 +274,42 @@ def test_oracle_render_is_deterministic_and_sample_ranges_compose():
     assert np.allclose((lo.astype(np.float64) + hi) / 2, a, rtol=1e-6, atol=1e-7)
     other, _ = sc.render(cam, seed=4)
     assert not np.array_equal(a, other)
+
+
+def test_moving_sphere_center_follows_ray_time():
+    """sphere.rs:110-111: center(t) = center + time*speed; :75-78: bbox = union of the boxes at time 0 and 1."""
+    from nr_ray_tracer_b200.scene_config import SceneGraph
+    g = SceneGraph()
+    t = g.add_texture(kind=A.TEX_SOLID, color=(1, 1, 1))
+    m = g.add_material(A.MAT_LAMBERTIAN, t)
+    s = g.add_object(A.OBJ_SPHERE, m, v=(0, 0, 0, 1, 2, 0, 0))   # speed (2, 0, 0)
+    g.root = g.add_object(A.OBJ_GROUP, children=[s])
+    sc = O.OracleScene(g)
+    rays = np.array([[1.5, 0, 5, 0, 0, -1],     # x = 1.5: outside at time 0, inside at time 0.5 (center x = 1)
+                     [0.0, 0, 5, 0, 0, -1]])    # x = 0: centre hit at time 0, miss at time 0.75 (center x = 1.5)
+    h0, _ = sc.trace_rays(rays, time=0.0)
+    assert np.isinf(h0["t"][0]) and h0["t"][1] == 4.0
+    h5, _ = sc.trace_rays(rays, time=0.5)
+    assert h5["t"][0] == 5.0 - np.sqrt(1.0 - 0.25)
+    np.testing.assert_allclose(h5["normal"][0], [0.5, 0, np.sqrt(0.75)], atol=1e-15)   # (point - center(t)) normalised
+    h75, _ = sc.trace_rays(rays, time=0.75)
+    assert np.isinf(h75["t"][1]) and np.isfinite(h75["t"][0])
+    # the render draws time per camera ray: the image of a moving sphere is a blur, not the static image
+    from nr_ray_tracer_b200.scene_config import CameraConfig
+    cfg = CameraConfig(width=48, height=27, samples_per_pixel=16, ray_max_bounces=4, look_from=(0.0, 0.0, 8.0),
+                       look_at=(0.0, 0.0, 0.0), background_color=(0.5, 0.7, 1.0)).to_builder_config()
+    cam = O.camera_build(cfg)
+    moving, _ = sc.render(cam, seed=3)
+    g2 = SceneGraph()
+    t2 = g2.add_texture(kind=A.TEX_SOLID, color=(1, 1, 1))
+    m2 = g2.add_material(A.MAT_LAMBERTIAN, t2)
+    g2.root = g2.add_object(A.OBJ_GROUP, children=[g2.add_object(A.OBJ_SPHERE, m2, v=(0, 0, 0, 1))])
+    static, _ = O.OracleScene(g2).render(cam, seed=3)
+    assert not np.array_equal(moving, static)
+    # Some(ZERO) speed behaves exactly like None
+    g3 = SceneGraph()
+    t3 = g3.add_texture(kind=A.TEX_SOLID, color=(1, 1, 1))
+    m3 = g3.add_material(A.MAT_LAMBERTIAN, t3)
+    g3.root = g3.add_object(A.OBJ_GROUP, children=[g3.add_object(A.OBJ_SPHERE, m3, v=(0, 0, 0, 1, 0, 0, 0))])
+    same, _ = O.OracleScene(g3).render(cam, seed=3)
+    assert np.array_equal(same, static)

@@ -197,7 +197,7 @@ def run_b200(args):
     cam = api.camera_build(graph.camera.to_builder_config())
     ctx = api.Context(local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    host = api.HostScene(graph)
+    host = api.HostScene(graph, bvh=args.bvh)
     ctx.upload(host)
     W, H = cam.width, cam.height
     fb = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
@@ -219,7 +219,7 @@ def run_b200(args):
 
     def step_e2e():
         """e2e: the public API call — host scene description in, host image out."""
-        h = api.HostScene(graph)         # reference BVH build + flatten (host)
+        h = api.HostScene(graph, bvh=args.bvh)   # BVH build + flatten (host)
         ctx.upload(h)                    # H2D of the flat scene
         _, st = ctx.render(cam, seed=0, mode=mode, rank=rank, world=world, rows_per_block=R,
                            out_device_ptr=fb.data_ptr())
@@ -363,7 +363,7 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": sum_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{SCENE} {args.width}x{args.height} {args.spp}spp depth{DEPTH}",
-                       "kernel_design": args.mode, "partition": f"row-blocks of {R}, round-robin over {world} GPU(s)",
+                       "kernel_design": args.mode, "bvh": args.bvh, "partition": f"row-blocks of {R}, round-robin over {world} GPU(s)",
                        "l2": "flushed between timed steps (256 MB write); the scene (KB-MB) is cache-resident by design, path "
                              "state lives in shared memory (fused) or streams through HBM (wavefront)",
                        "rng": "Philox4x32-10, seed 0"},
@@ -393,6 +393,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="fused", choices=["fused", "wavefront", "megakernel"])
+    ap.add_argument("--bvh", default="reference", choices=["reference", "sah"],
+                    help="reference = the reference's tree (parity contract, default); sah = opt-in SAH inner nodes")
     ap.add_argument("--scene", default=SCENE, help="scene file (default: the benchmark workload)")
     ap.add_argument("--depth", type=int, default=DEPTH)
     ap.add_argument("--width", type=int, default=WIDTH)

@@ -264,6 +264,16 @@ typedef struct nrrt_host_scene nrrt_host_scene;
  * flattens it.  `graph` is borrowed for the call only.  Returns NULL on error
  * (message via nrrt_host_last_error). */
 nrrt_host_scene* nrrt_host_build(const nrrt_graph_desc* graph);
+
+/* Same, with build options.  NRRT_BUILD_REFERENCE (0) is nrrt_host_build: the reference's tree, node for node.
+ * NRRT_BUILD_SAH replaces the inner nodes of every BVH::from tree by a binned surface-area-heuristic build
+ * (opt-in: the reference's median-split tree costs roughly twice the node visits on meshes).  Leaves, records
+ * and the depth-first leaf order that decides equal-t ties (object.rs:110-114) stay the reference's, so hits
+ * are the reference's except where a ray grazes a bounding box within f64 rounding: there the reference's
+ * result depends on which inner boxes its own tree tests (object.rs:102), and only the reference tree
+ * reproduces that. */
+enum { NRRT_BUILD_REFERENCE = 0, NRRT_BUILD_SAH = 1 };
+nrrt_host_scene* nrrt_host_build_ex(const nrrt_graph_desc* graph, uint32_t flags);
 const nrrt_scene_desc* nrrt_host_scene_desc(const nrrt_host_scene* scene);
 void nrrt_host_free(nrrt_host_scene* scene);
 const char* nrrt_host_last_error(void);

@@ -6,6 +6,7 @@ struct sizes against the values the compiled library reports.
 import ctypes as C
 
 ABI_VERSION = 3
+BUILD_REFERENCE, BUILD_SAH = 0, 1
 
 # status codes
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NO_SCENE, ERR_LIMIT, ERR_IO = 0, -1, -2, -3, -4, -5, -6

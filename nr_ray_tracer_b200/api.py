@@ -41,6 +41,8 @@ def lib() -> C.CDLL:
         L = C.CDLL(_LIB_PATH)
         L.nrrt_host_build.restype = C.c_void_p
         L.nrrt_host_build.argtypes = [C.POINTER(A.GraphDesc)]
+        L.nrrt_host_build_ex.restype = C.c_void_p
+        L.nrrt_host_build_ex.argtypes = [C.POINTER(A.GraphDesc), C.c_uint32]
         L.nrrt_host_scene_desc.restype = C.POINTER(A.SceneDesc)
         L.nrrt_host_scene_desc.argtypes = [C.c_void_p]
         L.nrrt_host_free.argtypes = [C.c_void_p]
@@ -123,14 +125,19 @@ class NativeScene:
 class HostScene:
     """Object graph -> reference BVH (objects/object.rs:41-73) -> flat device layout.  Pure host code."""
 
-    def __init__(self, graph):
-        """graph: a SceneGraph (Python loader) or a NativeScene (C++ loader)."""
+    def __init__(self, graph, bvh: str = "reference"):
+        """graph: a SceneGraph (Python loader) or a NativeScene (C++ loader).
+        bvh: "reference" = the reference's tree node for node (parity contract); "sah" = opt-in binned-SAH inner
+        nodes over the same leaves and leaf order (NRRT_BUILD_SAH, include/nrrt.h)."""
+        if bvh not in ("reference", "sah"):
+            raise ValueError("bvh must be 'reference' or 'sah'")
+        flags = A.BUILD_SAH if bvh == "sah" else A.BUILD_REFERENCE
         if isinstance(graph, NativeScene):
             self._holder = graph
-            self._h = lib().nrrt_host_build(C.byref(graph.graph))
+            self._h = lib().nrrt_host_build_ex(C.byref(graph.graph), flags)
         else:
             self._holder = graph.to_desc()
-            self._h = lib().nrrt_host_build(self._holder.ptr())
+            self._h = lib().nrrt_host_build_ex(self._holder.ptr(), flags)
         if not self._h:
             raise NrrtError(A.ERR_INVALID, lib().nrrt_host_last_error().decode())
         self.desc = lib().nrrt_host_scene_desc(self._h).contents
@@ -263,18 +270,19 @@ class Context:
 class Scene:
     """Drop-in for the reference's Scene (scene.rs:7-18): `Scene.load(path).render()`."""
 
-    def __init__(self, graph: SceneGraph, device: int = 0, ctx: Optional[Context] = None):
+    def __init__(self, graph: SceneGraph, device: int = 0, ctx: Optional[Context] = None, bvh: str = "reference"):
         self.graph = graph
         self.camera = camera_build(graph.camera.to_builder_config())
-        self.host = HostScene(graph)
+        self.host = HostScene(graph, bvh=bvh)
         self.ctx = ctx or Context(device)
         self.ctx.upload(self.host)
 
     @classmethod
     def load(cls, path: str, camera_override: Optional[CameraConfig] = None, base_dir: Optional[str] = None,
-             device: int = 0, ctx: Optional[Context] = None) -> "Scene":
+             device: int = 0, ctx: Optional[Context] = None, bvh: str = "reference") -> "Scene":
         """SceneConfig::try_load_scene + camera merge + try_build (render.rs:104-111)."""
-        return cls(load_scene(path, base_dir=base_dir, camera_override=camera_override), device=device, ctx=ctx)
+        return cls(load_scene(path, base_dir=base_dir, camera_override=camera_override), device=device, ctx=ctx,
+                   bvh=bvh)
 
     def render(self, progress: Optional[Callable[[int, int], None]] = None, **kw) -> np.ndarray:
         """Scene::render -> linear f32 RGB image (H, W, 3), no gamma, no clamp."""

@@ -120,6 +120,7 @@ static void usage() {
         "      --field-of-view <DEG>  --defocus-angle <DEG>  --focus-distance <D>\n"
         "      --samples-per-pixel <N>  --ray-max-bounces <N>\n"
         "      --seed <N>  --mode fused|wavefront|megakernel  --device <N>\n"
+        "      --bvh reference|sah   reference = the reference's BVH (default), sah = surface-area-heuristic inner nodes\n"
         "  -v, --verbose                  print timing\n"
         "Every camera option falls back to NR_RT_CAMERA_<NAME> (e.g. NR_RT_CAMERA_SAMPLES_PER_PIXEL).");
 }
@@ -130,7 +131,7 @@ int main(int argc, char** argv) {
         return argc < 2 ? 2 : 0;
     }
     if (std::strcmp(argv[1], "render") != 0) die(std::string("unknown command '") + argv[1] + "' (only `render` runs on the GPU path)");
-    std::string scene_path, output = "out.png", mode = "fused";
+    std::string scene_path, output = "out.png", mode = "fused", bvh = "reference";
     bool force = false, verbose = false;
     float gamma = 0.5f;  // constants.rs:1
     uint64_t seed = 0;
@@ -199,6 +200,7 @@ int main(int argc, char** argv) {
         else if (a == "--gamma-value") gamma = (float)std::atof(need());
         else if (a == "--seed") seed = std::strtoull(need(), nullptr, 10);
         else if (a == "--mode") mode = need();
+        else if (a == "--bvh") bvh = need();
         else if (a == "--device") device = std::atoi(need());
         else if (a == "-W") { if (!set_camera("width", need())) die("invalid width"); }
         else if (a == "-H") { if (!set_camera("height", need())) die("invalid height"); }
@@ -229,7 +231,8 @@ int main(int argc, char** argv) {
     if (nrrt_camera_file_to_config(&camf, &cfg) != NRRT_OK) die("image size needs exactly two of --width / --height / --aspect-ratio");
     nrrt_camera cam;
     if (nrrt_host_camera_build(&cfg, &cam) != NRRT_OK) die("bad camera configuration");
-    nrrt_host_scene* hs = nrrt_host_build(nrrt_loaded_graph(ls));
+    if (bvh != "reference" && bvh != "sah") die("--bvh must be reference or sah");
+    nrrt_host_scene* hs = nrrt_host_build_ex(nrrt_loaded_graph(ls), bvh == "sah" ? NRRT_BUILD_SAH : NRRT_BUILD_REFERENCE);
     if (!hs) die(nrrt_host_last_error());
     nrrt_ctx* ctx = nullptr;
     if (nrrt_create(device, &ctx) != NRRT_OK) die(nrrt_last_error(nullptr));

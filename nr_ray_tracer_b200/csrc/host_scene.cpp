@@ -81,7 +81,12 @@ struct Flattener {
     };
     std::map<uint32_t, SpaceRoot> space_memo;  // group object -> emitted space
 
-    explicit Flattener(const nrrt_graph_desc& graph) : g(graph), info(graph.n_objects) {}
+    // NRRT_BUILD_SAH (§8(f) N3): inner nodes come from a binned surface-area-heuristic build instead of the
+    // reference's median split.  Leaves, their records and their `order` numbers (the reference's depth-first leaf
+    // order, which decides equal-t ties) are emitted exactly as in the reference tree; only the inner nodes differ.
+    bool sah = false;
+
+    Flattener(const nrrt_graph_desc& graph, bool use_sah) : g(graph), info(graph.n_objects), sah(use_sah) {}
 
     const nrrt_object& obj(uint32_t i) const {
         if (i >= g.n_objects) fail("object index out of range");
@@ -270,20 +275,119 @@ struct Flattener {
         v.push_back(a.x), v.push_back(a.y), v.push_back(a.z);
     }
 
-    Emitted emit_bvh(uint32_t group, int n, SpaceCtx& sp) {
-        const ObjInfo& in = info[group];
-        const ObjInfo::BNode b = in.bvh[n];
+    // ---- NRRT_BUILD_SAH: leaves in reference DFS order, then a SAH tree over them
+    void collect_leaves(uint32_t group, int n, SpaceCtx& sp, std::vector<Emitted>& out) {
+        const ObjInfo::BNode b = info[group].bvh[n];
         if (b.leaf) {
-            if (b.object < 0) return Emitted{NRRT_REF_NONE, Aabb::empty(), 0, 0};
-            return emit_hitable((uint32_t)b.object, sp);  // Leaf(Some(o)) forwards, no box test (object.rs:95-97)
+            if (b.object >= 0) out.push_back(emit_hitable((uint32_t)b.object, sp));  // assigns sp.order in DFS order
+            return;
+        }
+        collect_leaves(group, b.left, sp, out);
+        collect_leaves(group, b.right, sp, out);
+    }
+    static double half_area(const Aabb& b) {
+        double dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+    static uint32_t ceil_log2(size_t n) {
+        uint32_t k = 0;
+        while (((size_t)1 << k) < n) ++k;
+        return k;
+    }
+    // Builds nodes over items[lo, hi) (hi - lo >= 2); depth_left bounds the subtree height so the traversal stack
+    // (NRRT_STACK_CAP, validated through max_stack) cannot overflow on adversarial inputs: when the budget gets
+    // tight the split falls back to the balanced median.
+    Emitted build_sah(std::vector<Emitted>& items, size_t lo, size_t hi, uint32_t depth_left) {
+        const size_t n = hi - lo;
+        Aabb box = items[lo].box, cbox = Aabb::empty();
+        for (size_t i = lo; i < hi; ++i) {
+            if (i > lo) box = box.unite(items[i].box);
+            for (int a = 0; a < 3; ++a) {
+                double c = 0.5 * (items[i].box.lo[a] + items[i].box.hi[a]);
+                cbox.lo[a] = std::fmin(cbox.lo[a], c), cbox.hi[a] = std::fmax(cbox.hi[a], c);
+            }
+        }
+        size_t mid = lo + n / 2;
+        int axis = 0;
+        for (int a = 1; a < 3; ++a)
+            if (cbox.hi[a] - cbox.lo[a] > cbox.hi[axis] - cbox.lo[axis]) axis = a;
+        auto centroid = [&](const Emitted& e, int a) { return 0.5 * (e.box.lo[a] + e.box.hi[a]); };
+        bool finite = true;
+        for (int a = 0; a < 3; ++a) finite = finite && std::isfinite(cbox.lo[a]) && std::isfinite(cbox.hi[a]);
+        bool median = n <= 2 || ceil_log2(n) + 1 >= depth_left || !finite || !(cbox.hi[axis] - cbox.lo[axis] > 0.0);
+        constexpr int NB = 16;
+        auto bin_of = [&](const Emitted& e, int a) {
+            return std::min(NB - 1, (int)((centroid(e, a) - cbox.lo[a]) / (cbox.hi[a] - cbox.lo[a]) * NB));
+        };
+        if (!median) {
+            double best_cost = std::numeric_limits<double>::infinity();
+            int best_axis = -1, best_bin = 0;
+            for (int a = 0; a < 3; ++a) {
+                if (!(cbox.hi[a] - cbox.lo[a] > 0.0)) continue;
+                Aabb bb[NB];
+                size_t cnt[NB] = {0};
+                for (int k = 0; k < NB; ++k) bb[k] = Aabb::empty();
+                for (size_t i = lo; i < hi; ++i) {
+                    int k = bin_of(items[i], a);
+                    for (int x = 0; x < 3; ++x) {
+                        bb[k].lo[x] = std::fmin(bb[k].lo[x], items[i].box.lo[x]);
+                        bb[k].hi[x] = std::fmax(bb[k].hi[x], items[i].box.hi[x]);
+                    }
+                    cnt[k]++;
+                }
+                double right_area[NB];
+                size_t right_cnt[NB];
+                Aabb acc = Aabb::empty();
+                size_t c = 0;
+                for (int k = NB - 1; k > 0; --k) {
+                    if (cnt[k])
+                        for (int x = 0; x < 3; ++x)
+                            acc.lo[x] = std::fmin(acc.lo[x], bb[k].lo[x]), acc.hi[x] = std::fmax(acc.hi[x], bb[k].hi[x]);
+                    c += cnt[k];
+                    right_area[k] = c ? half_area(acc) : 0.0;
+                    right_cnt[k] = c;
+                }
+                acc = Aabb::empty();
+                c = 0;
+                for (int k = 0; k < NB - 1; ++k) {
+                    if (cnt[k])
+                        for (int x = 0; x < 3; ++x)
+                            acc.lo[x] = std::fmin(acc.lo[x], bb[k].lo[x]), acc.hi[x] = std::fmax(acc.hi[x], bb[k].hi[x]);
+                    c += cnt[k];
+                    if (c == 0 || right_cnt[k + 1] == 0) continue;
+                    double cost = half_area(acc) * (double)c + right_area[k + 1] * (double)right_cnt[k + 1];
+                    if (cost < best_cost) best_cost = cost, best_axis = a, best_bin = k;
+                }
+            }
+            if (best_axis < 0) {
+                median = true;
+            } else {
+                auto first_right = std::stable_partition(items.begin() + lo, items.begin() + hi, [&](const Emitted& e) {
+                    return bin_of(e, best_axis) <= best_bin;
+                });
+                mid = (size_t)(first_right - items.begin());
+                if (mid == lo || mid == hi) median = true;
+            }
+        }
+        if (median) {
+            if (finite)
+                std::stable_sort(items.begin() + lo, items.begin() + hi, [&](const Emitted& x, const Emitted& y) {
+                    return centroid(x, axis) < centroid(y, axis);
+                });
+            mid = lo + n / 2;
         }
         uint32_t idx = (uint32_t)nodes.size();
         if (idx >= NRRT_REF_INDEX_MASK) fail("too many BVH nodes");
         nodes.emplace_back();
         child_boxes.emplace_back();
         child_boxes.emplace_back();
-        Emitted l = emit_bvh(group, b.left, sp);   // left first: DFS leaf order
-        Emitted r = emit_bvh(group, b.right, sp);
+        const uint32_t dl = depth_left > 1 ? depth_left - 1 : 1;
+        Emitted l = (mid - lo == 1) ? items[lo] : build_sah(items, lo, mid, dl);
+        Emitted r = (hi - mid == 1) ? items[mid] : build_sah(items, mid, hi, dl);
+        write_node(idx, l, r);
+        return Emitted{NRRT_REF(NRRT_REF_NODE, idx), box, 1 + std::max(l.depth, r.depth), std::max(l.levels, r.levels)};
+    }
+    void write_node(uint32_t idx, const Emitted& l, const Emitted& r) {
         nrrt_node nd;
         std::memset(&nd, 0, sizeof nd);
         const Emitted* ch[2] = {&l, &r};
@@ -296,6 +400,31 @@ struct Flattener {
             child_boxes[2 * (size_t)idx + c] = to_box(ch[c]->box);
         }
         nodes[idx] = nd;
+    }
+    Emitted emit_group_sah(uint32_t group, SpaceCtx& sp) {
+        std::vector<Emitted> items;
+        collect_leaves(group, info[group].bvh_root, sp, items);
+        if (items.empty()) return Emitted{NRRT_REF_NONE, Aabb::empty(), 0, 0};
+        if (items.size() == 1) return items[0];
+        return build_sah(items, 0, items.size(), ceil_log2(items.size()) + 7);
+    }
+
+    Emitted emit_bvh(uint32_t group, int n, SpaceCtx& sp) {
+        const ObjInfo& in = info[group];
+        if (sah && n == in.bvh_root && !in.bvh[n].leaf) return emit_group_sah(group, sp);
+        const ObjInfo::BNode b = in.bvh[n];
+        if (b.leaf) {
+            if (b.object < 0) return Emitted{NRRT_REF_NONE, Aabb::empty(), 0, 0};
+            return emit_hitable((uint32_t)b.object, sp);  // Leaf(Some(o)) forwards, no box test (object.rs:95-97)
+        }
+        uint32_t idx = (uint32_t)nodes.size();
+        if (idx >= NRRT_REF_INDEX_MASK) fail("too many BVH nodes");
+        nodes.emplace_back();
+        child_boxes.emplace_back();
+        child_boxes.emplace_back();
+        Emitted l = emit_bvh(group, b.left, sp);   // left first: DFS leaf order
+        Emitted r = emit_bvh(group, b.right, sp);
+        write_node(idx, l, r);
         return Emitted{NRRT_REF(NRRT_REF_NODE, idx), b.box, 1 + std::max(l.depth, r.depth), std::max(l.levels, r.levels)};
     }
 
@@ -411,8 +540,14 @@ extern "C" {
 
 const char* nrrt_host_last_error(void) { return g_error.c_str(); }
 
-nrrt_host_scene* nrrt_host_build(const nrrt_graph_desc* g) {
+nrrt_host_scene* nrrt_host_build(const nrrt_graph_desc* g) { return nrrt_host_build_ex(g, NRRT_BUILD_REFERENCE); }
+
+nrrt_host_scene* nrrt_host_build_ex(const nrrt_graph_desc* g, uint32_t flags) {
     g_error.clear();
+    if (flags & ~(uint32_t)NRRT_BUILD_SAH) {
+        g_error = "nrrt_host_build_ex: unknown flags";
+        return nullptr;
+    }
     if (!g || !g->objects || g->root >= g->n_objects) {
         g_error = "nrrt_host_build: null graph or bad root";
         return nullptr;
@@ -434,7 +569,7 @@ nrrt_host_scene* nrrt_host_build(const nrrt_graph_desc* g) {
             if (t.kind == NRRT_TEX_IMAGE && t.a >= g->n_images) fail("image index out of range");
         }
         auto hs = std::make_unique<nrrt_host_scene>();
-        hs->f = std::make_unique<Flattener>(*g);
+        hs->f = std::make_unique<Flattener>(*g, (flags & NRRT_BUILD_SAH) != 0);
         Flattener& f = *hs->f;
         f.prepare(g->root, 0);
         Flattener::SpaceCtx world;

@@ -109,8 +109,11 @@ def _mat4(m, v, point):
     return r
 
 
-def trace(fs: FlatScene, o, d, tmin=0.001, tmax=INF):
-    """Returns (t, object index, order path) of the reference's winner, or None."""
+def trace(fs: FlatScene, o, d, tmin=0.001, tmax=INF, tie_by_order=False):
+    """Returns (t, object index, leaf order in the current space) of the reference's winner, or None.
+    tie_by_order=False: equal-t ties go to the later child of the flat tree (the reference rule on the reference
+    tree).  tie_by_order=True: ties go to the leaf with the larger reference DFS order — what the kernels do, and
+    the only rule that is right on an NRRT_BUILD_SAH tree, whose child order is not the reference's."""
 
     def hit_ref(ref, o, d):
         ty, ix = ref >> A.REF_TYPE_SHIFT, ref & A.REF_INDEX_MASK
@@ -128,7 +131,11 @@ def trace(fs: FlatScene, o, d, tmin=0.001, tmax=INF):
                     if not box_hit(lo, hi, o, d, tmin, tmax):
                         continue
                 h = hit_ref(cref, o, d)
-                if h is not None and (res is None or not (res[0] < h[0])):  # ties -> right (later) child
+                if h is None:
+                    continue
+                if res is None or h[0] < res[0]:
+                    res = h
+                elif h[0] == res[0] and (h[2] > res[2] if tie_by_order else True):  # ties -> later leaf
                     res = h
             return res
         if ty == A.REF_SPHERE:
@@ -145,7 +152,7 @@ def trace(fs: FlatScene, o, d, tmin=0.001, tmax=INF):
                 t = _div(h + sq, a)
                 if not (tmin < t < tmax):
                     return None
-            return (t, int(fs.sobj[ix]))
+            return (t, int(fs.sobj[ix]), int(fs.so[ix]))
         if ty == A.REF_PLANE:
             n = fs.pn[ix]
             denom = _dot(n, d)
@@ -161,7 +168,7 @@ def trace(fs: FlatScene, o, d, tmin=0.001, tmax=INF):
                 ok = alpha > 0.0 and beta > 0.0 and (alpha + beta) < 1.0
             else:
                 ok = 0.0 <= alpha <= 1.0 and 0.0 <= beta <= 1.0
-            return (t, int(fs.pobj[ix])) if ok else None
+            return (t, int(fs.pobj[ix]), int(fs.po[ix])) if ok else None
         if ty == A.REF_INSTANCE:
             ins = fs.inst[ix]
             oo, dd = list(o), list(d)
@@ -180,7 +187,8 @@ def trace(fs: FlatScene, o, d, tmin=0.001, tmax=INF):
             if (inner >> A.REF_TYPE_SHIFT) == A.REF_NODE:
                 if not box_hit(list(ins.inner_box.lo), list(ins.inner_box.hi), oo, dd, tmin, tmax):
                     return None
-            return hit_ref(inner, oo, dd)
+            h = hit_ref(inner, oo, dd)
+            return None if h is None else (h[0], h[1], int(fs.inst_order[ix]))
         return None
 
     root = fs.root

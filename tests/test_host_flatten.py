@@ -195,3 +195,47 @@ def test_moving_sphere_bbox_is_union_of_both_shutter_ends_and_speed_is_exported(
     g2.root = g2.add_object(A.OBJ_GROUP, children=[g2.add_object(A.OBJ_SPHERE, m2, v=(0, 0, 0, 1, 0, 0, 0)),
                                                    g2.add_object(A.OBJ_SPHERE, m2, v=(3, 0, 0, 1))])
     assert not bool(api.HostScene(g2).desc.sphere_speed)
+
+
+@pytest.mark.parametrize("name", ["spheres.toml", "cornell-box-scene.json", "cube-scene.json", "utah-teapot-scene.json"])
+def test_sah_build_keeps_leaves_and_order_and_gives_oracle_hits(name):
+    """NRRT_BUILD_SAH (§8(f) N3): same leaves, records and reference DFS order numbers; only inner nodes differ.
+    Traversed with the reference's box / primitive tests and order-based tie-break it returns the oracle's hits."""
+    g = load(name)
+    ref_hs, hs = api.HostScene(g), api.HostScene(g, bvh="sah")
+    a, b = ref_hs.desc, hs.desc
+    assert (a.n_nodes, a.n_spheres, a.n_planes, a.n_instances) == (b.n_nodes, b.n_spheres, b.n_planes, b.n_instances)
+    for field, n in (("sphere_order", a.n_spheres), ("plane_order", a.n_planes), ("instance_order", a.n_instances),
+                     ("sphere_object", a.n_spheres), ("plane_object", a.n_planes)):
+        if n:
+            assert np.array_equal(np.ctypeslib.as_array(getattr(a, field), shape=(n,)),
+                                  np.ctypeslib.as_array(getattr(b, field), shape=(n,))), field
+    assert list(a.root_box.lo) == list(b.root_box.lo) and list(a.root_box.hi) == list(b.root_box.hi)
+    assert b.max_stack <= 32
+    # every leaf is referenced exactly once by the SAH nodes, and child boxes enclose their subtrees
+    nodes = hs.nodes()
+    refs = nodes["child"].reshape(-1)
+    leaves = refs[(refs >> A.REF_TYPE_SHIFT) != A.REF_NODE]
+    assert len(set(leaves.tolist())) == len(leaves)
+    if name != "spheres.toml":
+        assert not np.array_equal(nodes["child"], ref_hs.nodes()["child"])   # it really is another tree
+    fs = flat_interp.FlatScene(hs)
+    rays = np.concatenate([kat.random_rays(g, 300, seed=5), kat.aimed_rays(g, 500, seed=6)])
+    ref, _ = O.OracleScene(g).trace_rays(rays)
+    for i, r in enumerate(rays):
+        h = flat_interp.trace(fs, r[:3], r[3:], tie_by_order=True)
+        if ref["object"][i] == 0xFFFFFFFF:
+            assert h is None, (i, r, h)
+        else:
+            assert h is not None and h[1] == ref["object"][i] and h[0] == ref["t"][i], (i, r, h, ref[i])
+
+
+def test_sah_surface_area_cost_is_lower_than_median_split_on_the_mesh():
+    g = load("utah-teapot-scene.json")
+
+    def sah_cost(hs):
+        cb = hs.child_boxes()                      # (n, 2, 2, 3)
+        ext = cb[:, :, 1, :] - cb[:, :, 0, :]
+        area = ext[..., 0] * ext[..., 1] + ext[..., 1] * ext[..., 2] + ext[..., 2] * ext[..., 0]
+        return float(area.sum())                   # sum of child-box areas ~ expected node + leaf visits
+    assert sah_cost(api.HostScene(g, bvh="sah")) < 0.8 * sah_cost(api.HostScene(g))

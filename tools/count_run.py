@@ -6,8 +6,8 @@ from nr_ray_tracer_b200 import api
 from nr_ray_tracer_b200.scene_config import CameraConfig, load_scene
 ctx = api.Context(0)
 for name in sys.argv[1:] or ["cornell-box-scene.json", "spheres.toml", "utah-teapot-scene.json", "earth.toml", "noise.toml"]:
-    g = load_scene("scenes/" + name, camera_override=CameraConfig(width=960, height=540, samples_per_pixel=4, ray_max_bounces=50))
-    hs = api.HostScene(g); ctx.upload(hs)
+    g = load_scene("scenes/" + name, camera_override=CameraConfig(width=960, height=540, samples_per_pixel=4, ray_max_bounces=int(os.environ.get("DEPTH", "50"))))
+    hs = api.HostScene(g, bvh=os.environ.get("BVH", "reference")); ctx.upload(hs)
     cam = api.camera_build(g.camera.to_builder_config())
     _, st = ctx.render(cam, seed=1, count=True)
     s = st["segments"]

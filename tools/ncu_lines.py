@@ -3,7 +3,9 @@
 
 ncu's CSV source page is SASS-only; this joins it (in instruction order) with `nvdisasm -g` line info of the
 same kernel in the in-tree library, and prints the hottest source lines.
-Usage: ncu_lines.py rep.ncu-rep <kernel-regex> [top_n]
+Usage: ncu_lines.py rep.ncu-rep <kernel-regex> [top_n] [mangled-regex]
+The optional mangled-regex picks the template instantiation in the library (e.g. k_render_fusedILj6ELi4E) when
+the demangled kernel regex given to ncu matches several.
 """
 import collections
 import csv
@@ -63,7 +65,7 @@ def main():
             rows.append((r[si].strip(), int(r[ii]), int(r[ti]), int(r[wi])))
         except (ValueError, IndexError):
             pass
-    dis = disasm_lines(kre)
+    dis = disasm_lines(sys.argv[4] if len(sys.argv) > 4 else kre)
     if len(dis) != len(rows):
         print(f"warning: {len(rows)} profiled instructions vs {len(dis)} disassembled (library rebuilt since the "
               f"profile?) — attribution by position may be off", file=sys.stderr)

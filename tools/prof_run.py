@@ -13,7 +13,7 @@ mode = {"mega": A.MODE_MEGAKERNEL, "wavefront": A.MODE_WAVEFRONT}.get(sys.argv[3
 ctx = api.Context(0)
 g = load_scene("scenes/" + name, camera_override=CameraConfig(width=1920, height=1080, samples_per_pixel=spp,
                                                               ray_max_bounces=50))
-hs = api.HostScene(g)
+hs = api.HostScene(g, bvh=os.environ.get("BVH", "reference"))
 ctx.upload(hs)
 cam = api.camera_build(g.camera.to_builder_config())
 img, st = ctx.render(cam, seed=1, mode=mode)

@@ -44,7 +44,7 @@ def main():
     for name, scene, W, H, spp, depth, cpu_spp in CONFIGS:
         gpu_spp = max(1, spp // 16) if quick else spp
         g = load_scene(scene, camera_override=CameraConfig(width=W, height=H, samples_per_pixel=gpu_spp, ray_max_bounces=depth))
-        host = api.HostScene(g)
+        host = api.HostScene(g, bvh=os.environ.get("BVH", "reference"))
         ctx.upload(host)
         cam = api.camera_build(g.camera.to_builder_config())
         fb = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")

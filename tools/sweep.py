@@ -15,7 +15,7 @@ def main():
         name, spp = spec.split(":")
         g = load_scene("scenes/" + name, camera_override=CameraConfig(width=1920, height=1080, samples_per_pixel=int(spp),
                                                                       ray_max_bounces=50))
-        hs = api.HostScene(g)
+        hs = api.HostScene(g, bvh=os.environ.get("BVH", "reference"))
         ctx.upload(hs)
         cam = api.camera_build(g.camera.to_builder_config())
         ref = None

@@ -116,7 +116,7 @@ k_trace_rays(const __grid_constant__ DevScene S, const double* __restrict__ rays
     r.prim = h.prim;
     r.depth = h.depth;
 #pragma unroll
-    for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) r.inst[k] = h.inst[k];
+    for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) r.inst[k] = h.inst.get(k);
     r._pad = 0;
     if (h.prim != NRRT_REF_NONE) {
         HitRec rec;
@@ -567,9 +567,9 @@ k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState 
                      has) && has) {
             W.hit_t[slot] = tr.best.t;
             W.hit_prim[slot] = tr.best.prim;
-            if (F & NRRT_F_INSTANCES) W.hit_inst[slot] = tr.best.depth | (tr.best.inst[0] << 3);
+            if (F & NRRT_F_INSTANCES) W.hit_inst[slot] = tr.best.depth | (tr.best.inst.a << 3);
             if ((F & NRRT_F_INSTANCES) && tr.best.depth > 1)
-                for (uint32_t l = 1; l < tr.best.depth; ++l) W.hit_inst[(size_t)l * n + slot] = tr.best.inst[l];
+                for (uint32_t l = 1; l < tr.best.depth; ++l) W.hit_inst[(size_t)l * n + slot] = tr.best.inst.get(l);
             has = false;
         }
     }
@@ -610,10 +610,11 @@ k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_came
         {
             const uint32_t w0 = (!(F & NRRT_F_INSTANCES) || h.prim == NRRT_REF_NONE) ? 0u : W.hit_inst[slot];
             h.depth = w0 & 7u;
-            h.inst[0] = w0 >> 3;
+            h.inst.clear();
+            h.inst.a = w0 >> 3;
 #pragma unroll
             for (uint32_t l = 1; l < NRRT_MAX_INSTANCE_DEPTH; ++l)
-                h.inst[l] = ((F & NRRT_F_INSTANCES) && l < h.depth) ? W.hit_inst[(size_t)l * n + slot] : 0u;
+                h.inst.set(l, ((F & NRRT_F_INSTANCES) && l < h.depth) ? W.hit_inst[(size_t)l * n + slot] : 0u);
         }
 #if !NRRT_HIT_SINK
         survive = path_step(S, cam, h, smp, o, d, W.ray[6 * (size_t)n + slot], T, L, bounce);

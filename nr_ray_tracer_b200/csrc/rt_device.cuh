@@ -244,11 +244,22 @@ __device__ __forceinline__ double plane_t(const DevScene& S, uint32_t i, d3 o, d
 }
 
 // --------------------------------------------------------------------------- closest hit
+// Instance chain of a leaf (one id per nesting level).  Scalar members with select-based accessors instead of an
+// array: an array member that is ever indexed dynamically pins the whole enclosing state struct in local memory.
+static_assert(NRRT_MAX_INSTANCE_DEPTH == 4, "InstChain has four members");
+struct InstChain {
+    uint32_t a, b, c, d;
+    __device__ __forceinline__ uint32_t get(uint32_t k) const { return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d)); }
+    __device__ __forceinline__ void set(uint32_t k, uint32_t v) {
+        a = k == 0 ? v : a, b = k == 1 ? v : b, c = k == 2 ? v : c, d = k == 3 ? v : d;
+    }
+    __device__ __forceinline__ void clear() { a = b = c = d = 0; }
+};
 struct HitId {
     double t;        // +inf = miss
     uint32_t prim;   // NRRT_REF_NONE = miss
     uint32_t depth;  // instance levels above prim
-    uint32_t inst[NRRT_MAX_INSTANCE_DEPTH];
+    InstChain inst;
 };
 
 struct TraceCounters {
@@ -264,12 +275,14 @@ __device__ __forceinline__ uint32_t leaf_order(const DevScene& S, uint32_t ref) 
 
 // Equal-t tie: the reference keeps the right child (object.rs:110-114), i.e. the candidate that comes
 // later in depth-first leaf order wins.  Compare the two leaf paths level by level.
-__device__ __noinline__ bool tie_candidate_wins(const DevScene& S, uint32_t cand, const uint32_t* cur_inst,
-                                                uint32_t level, const HitId& best) {
+// Both instance chains come BY VALUE: passing pointers into the traversal state would pin the whole state struct in
+// local memory (the compiler cannot split an object whose interior address escapes into a call).
+__device__ __noinline__ bool tie_candidate_wins(const DevScene& S, uint32_t cand, InstChain cur_chain, uint32_t level,
+                                                InstChain best_chain, uint32_t best_prim, uint32_t best_depth) {
     for (uint32_t l = 0;; ++l) {
-        bool ca = l < level, cb = l < best.depth;
-        uint32_t ra = ca ? NRRT_REF(NRRT_REF_INSTANCE, cur_inst[l]) : cand;
-        uint32_t rb = cb ? NRRT_REF(NRRT_REF_INSTANCE, best.inst[l]) : best.prim;
+        bool ca = l < level, cb = l < best_depth;
+        uint32_t ra = ca ? NRRT_REF(NRRT_REF_INSTANCE, cur_chain.get(l)) : cand;
+        uint32_t rb = cb ? NRRT_REF(NRRT_REF_INSTANCE, best_chain.get(l)) : best_prim;
         if (ra != rb) return leaf_order(S, ra) > leaf_order(S, rb);
         if (!ca || !cb) return false;  // same leaf
     }
@@ -386,7 +399,7 @@ struct Traversal {
     Ray32 r32;
     float tcull;
     uint32_t sp, cur, level;
-    uint32_t cur_inst[NRRT_MAX_INSTANCE_DEPTH];
+    InstChain cur_inst;
     HitId best;
 
     // the ray in the current space: from the traversal state, or from the context when it owns it
@@ -419,8 +432,8 @@ struct Traversal {
         best.t = NRRT_INF;
         best.prim = NRRT_REF_NONE;
         best.depth = 0;
-#pragma unroll
-        for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) best.inst[k] = 0, cur_inst[k] = 0;
+        best.inst.clear();
+        cur_inst.clear();
         level = 0;
         d3 wo, wd;
         ctx.get(wo, wd);
@@ -519,15 +532,12 @@ struct Traversal {
             }
             if (t == t) {
                 bool take = t < best.t;
-                if (!take && t == best.t) take = tie_candidate_wins(S, cur, cur_inst, level, best);
+                if (!take && t == best.t) take = tie_candidate_wins(S, cur, cur_inst, level, best.inst, best.prim, best.depth);
                 if (take) {
                     best.t = t;
                     best.prim = cur;
                     best.depth = level;
-                    if ((F & NRRT_F_INSTANCES) && level) {
-#pragma unroll
-                        for (int k = 0; k < NRRT_MAX_INSTANCE_DEPTH; ++k) best.inst[k] = cur_inst[k];
-                    }
+                    if ((F & NRRT_F_INSTANCES) && level) best.inst = cur_inst;
                     ctx.put(level, pt, a_, b_, d);
                     // f32 upper bound of t with slack far above any f64 rounding discrepancy
                     float tf = (float)t;
@@ -551,7 +561,7 @@ struct Traversal {
                 if (enter) {
                     stack[sp * sstride] = NRRT_REF_POP;
                     ++sp;
-                    cur_inst[level] = ii;
+                    cur_inst.set(level, ii);
                     ++level;
                     store_ray(ctx, no, nd);
                     r32 = n32;
@@ -578,7 +588,9 @@ struct Traversal {
             --level;
             d3 po, pd;
             ctx.get(po, pd);
-            for (uint32_t l = 0; l < level; ++l) instance_ray(S, cur_inst[l], po, pd);
+#pragma unroll
+            for (int l = 0; l < NRRT_MAX_INSTANCE_DEPTH; ++l)
+                if (l < (int)level) instance_ray(S, cur_inst.get(l), po, pd);
             store_ray(ctx, po, pd);
             r32 = make_ray32(po, pd);
         }
@@ -614,7 +626,9 @@ struct HitRec {
 __device__ __forceinline__ void resolve_hit(const DevScene& S, const HitId& h, d3 wo, d3 wd, double time, bool want_uv,
                                             HitRec& rec) {
     d3 o = wo, d = wd;
-    for (uint32_t l = 0; l < h.depth; ++l) instance_ray(S, h.inst[l], o, d);
+#pragma unroll
+    for (int l = 0; l < NRRT_MAX_INSTANCE_DEPTH; ++l)
+        if (l < (int)h.depth) instance_ray(S, h.inst.get(l), o, d);
     uint32_t ty = NRRT_REF_TYPE(h.prim), ix = NRRT_REF_INDEX(h.prim);
     d3 point = ray_at(o, d, h.t), outward;
     double u = 0.0, v = 0.0;
@@ -641,7 +655,9 @@ __device__ __forceinline__ void resolve_hit(const DevScene& S, const HitId& h, d
     double sign = signum(dot3(d, outward));
     rec.front_face = sign < 0.0;
     d3 normal = scale3(outward, -sign);
-    for (uint32_t l = h.depth; l-- > 0;) instance_hit_back(S, h.inst[l], point, normal);
+#pragma unroll
+    for (int l = NRRT_MAX_INSTANCE_DEPTH - 1; l >= 0; --l)
+        if (l < (int)h.depth) instance_hit_back(S, h.inst.get(l), point, normal);
     rec.point = point;
     rec.normal = normal;
     rec.u = u;
@@ -677,7 +693,11 @@ __device__ __forceinline__ void resolve_hit_attr(const DevScene& S, const HitId&
     rec.front_face = sign < 0.0;
     d3 normal = scale3(outward, -sign);
     if (F & NRRT_F_INSTANCES)
-        for (uint32_t l = h.depth; l-- > 0;) instance_hit_back(S, h.inst[l], point, normal);
+    {
+#pragma unroll
+        for (int l = NRRT_MAX_INSTANCE_DEPTH - 1; l >= 0; --l)
+            if (l < (int)h.depth) instance_hit_back(S, h.inst.get(l), point, normal);
+    }
     rec.point = point;
     rec.normal = normal;
     rec.u = u;

@@ -531,8 +531,11 @@ k_wf_init(const __grid_constant__ nrrt_camera cam, const __grid_constant__ Rende
 #ifndef NRRT_REFILL_MIN
 #define NRRT_REFILL_MIN 16  // refill once this many lanes of the warp are idle (8/16 measured: 16 wins on Cornell + teapot)
 #endif
+#ifndef NRRT_EXTEND_MINBLOCKS
+#define NRRT_EXTEND_MINBLOCKS 4  // resident blocks per SM the traverse kernel is compiled for (5 spills since the state moved to registers)
+#endif
 template <uint32_t F>
-__global__ void __launch_bounds__(NRRT_BLOCK, 5)
+__global__ void __launch_bounds__(NRRT_BLOCK, NRRT_EXTEND_MINBLOCKS)
 k_wf_extend(const __grid_constant__ DevScene S, const __grid_constant__ WfState W, uint32_t n, uint32_t qin) {
     extern __shared__ uint32_t s_stack[];
     const uint32_t lane = threadIdx.x & 31u;
@@ -815,7 +818,7 @@ int nrrt_create(int device, nrrt_ctx** out) {
     {
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
-            ctx->persistent_blocks = (unsigned)sms * 5u;
+            ctx->persistent_blocks = (unsigned)sms * NRRT_EXTEND_MINBLOCKS;
     }
     if ((e = cudaMalloc((void**)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess)
         return bail("cudaMalloc", e);
@@ -1198,7 +1201,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     const bool wavefront = o.mode == NRRT_MODE_WAVEFRONT && !counting;
     const bool fused = o.mode == NRRT_MODE_FUSED && !counting;
     if (fused) {  // persistent: one thread per resident lane; the work counter hands out the rest
-        const uint64_t resident = (uint64_t)(ctx->persistent_blocks / 5) * NRRT_FUSED_BLOCKS_PER_SM * NRRT_BLOCK;
+        const uint64_t resident = (uint64_t)(ctx->persistent_blocks / NRRT_EXTEND_MINBLOCKS) * NRRT_FUSED_BLOCKS_PER_SM * NRRT_BLOCK;
         P.n_slots = (uint32_t)std::min<uint64_t>(n_items64, o.max_slots ? std::min<uint64_t>(o.max_slots, resident) : resident);
     }
     const size_t fb_bytes = (size_t)total_pixels * 3 * sizeof(float);

@@ -801,21 +801,18 @@ __device__ __forceinline__ d3 random_in_unit_disk(const Sampler& s) {
 
 // --------------------------------------------------------------------------- textures
 // noise 0.9.0 Perlin (restated from the published algorithm).
+// Gradient dot product, branch-free (the hash differs per lane: a 12-way switch would serialise the warp eight
+// times per octave).  h & 15: 0-3 = (+-x) +- y, 4-7 = (+-x) +- z, 8-11 = (+-y) +- z, 12-15 repeat 0, 1, 9, 11; bit 0
+// negates the first term, bit 1 subtracts the second.  Every result is one exact IEEE add or subtract of the same
+// operands as the table form, so the value is bit-identical.
 __device__ __forceinline__ double grad3(uint32_t h, double x, double y, double z) {
-    switch (h & 15u) {
-        case 0: case 12: return xadd(x, y);
-        case 1: case 13: return xadd(-x, y);
-        case 2: return xsub(x, y);
-        case 3: return xsub(-x, y);
-        case 4: return xadd(x, z);
-        case 5: return xadd(-x, z);
-        case 6: return xsub(x, z);
-        case 7: return xsub(-x, z);
-        case 8: return xadd(y, z);
-        case 9: case 14: return xadd(-y, z);
-        case 10: return xsub(y, z);
-        default: return xsub(-y, z);
-    }
+    h &= 15u;
+    const uint32_t k = h < 12u ? h : ((0xB910u >> ((h - 12u) * 4u)) & 15u);  // 12 -> 0, 13 -> 1, 14 -> 9, 15 -> 11
+    const uint32_t g = k >> 2;
+    const double a = g == 2u ? y : x;
+    const double b = g == 0u ? y : z;
+    const double sa = (k & 1u) ? -a : a;
+    return (k & 2u) ? xsub(sa, b) : xadd(sa, b);
 }
 __device__ __forceinline__ double quintic(double t) {
     return xmul(xmul(xmul(t, t), t), xadd(xmul(t, xsub(xmul(t, 6.0), 15.0)), 10.0));

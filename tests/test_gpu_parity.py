@@ -433,3 +433,54 @@ def test_sah_bvh_option_gives_the_reference_result(gpu_ctx, name):
     assert np.array_equal(out["sah"][2], out["reference"][2])
     if name == "utah-teapot-scene.json":
         assert out["sah"][1]["node_visits"] < 0.8 * out["reference"][1]["node_visits"]
+
+
+def test_large_mesh_stress(gpu_ctx):
+    """45 k triangles (a wavy height field behind wrappers, plus spheres): deep trees, the speculative traversal,
+    the stack budget and both BVH builds, against the oracle."""
+    from nr_ray_tracer_b200.scene_config import CameraConfig, SceneGraph
+    g = SceneGraph()
+    t = g.add_texture(kind=A.TEX_SOLID, color=(0.6, 0.7, 0.5))
+    m = g.add_material(A.MAT_LAMBERTIAN, t)
+    mm = g.add_material(A.MAT_METAL, t, 0.1)
+    n = 150
+    xs = np.linspace(-5, 5, n + 1)
+    h = lambda x, z: 0.4 * np.sin(1.7 * x) * np.cos(1.3 * z) + 0.05 * np.sin(9 * x + 4 * z)   # noqa: E731
+    tris = []
+    for i in range(n):
+        for j in range(n):
+            x0, x1, z0, z1 = xs[i], xs[i + 1], xs[j], xs[j + 1]
+            p00, p10 = (x0, h(x0, z0), z0), (x1, h(x1, z0), z0)
+            p01, p11 = (x0, h(x0, z1), z1), (x1, h(x1, z1), z1)
+            for a, b, c in ((p00, p10, p01), (p11, p01, p10)):
+                u, v = np.subtract(b, a), np.subtract(c, a)
+                tris.append(g.add_object(A.OBJ_TRIANGLE, m, v=(*a, *u, *v)))
+    mesh = g.add_object(A.OBJ_GROUP, children=tris)
+    inst = g.add_object(A.OBJ_TRANSLATE, children=[g.add_object(A.OBJ_ROTATE_Y, children=[mesh], v=(0.3,))], v=(0, -1, 0))
+    balls = [g.add_object(A.OBJ_SPHERE, mm, v=(float(k) - 2.0, 0.6, 0.5 * k, 0.4)) for k in range(5)]
+    g.root = g.add_object(A.OBJ_GROUP, children=[inst] + balls)
+    g.camera = CameraConfig(width=160, height=90, samples_per_pixel=4, ray_max_bounces=6, look_from=(0.0, 3.0, 9.0),
+                            look_at=(0.0, -0.5, 0.0), background_color=(0.6, 0.7, 1.0), field_of_view=50.0)
+    cam = api.camera_build(g.camera.to_builder_config())
+    rays = np.concatenate([kat.aimed_rays(g, 50000), kat.random_rays(g, 50000)])
+    osc = O.OracleScene(g)
+    ref, _ = osc.trace_rays(rays)
+    ref_img, cnt = osc.render(O.camera_build(g.camera.to_builder_config()), seed=4)
+    imgs = {}
+    for bvh in ("reference", "sah"):
+        hs = api.HostScene(g, bvh=bvh)
+        assert hs.desc.n_planes == 2 * n * n and hs.desc.max_stack <= 32
+        gpu_ctx.upload(hs)
+        for visit_all in (False, True):
+            gpu, _ = gpu_ctx.trace_rays(rays, visit_all=visit_all)
+            res = kat.compare_hits(gpu, ref)
+            assert kat.hits_ok(res) and res["hits"] > 20000, (bvh, visit_all, res)
+        for mode, mname in MODES:
+            img, st = gpu_ctx.render(cam, seed=4, mode=mode)
+            assert st["segments"] == cnt["segments"], (bvh, mname)
+            imgs[(bvh, mname)] = img
+        del hs
+    first = imgs[("reference", "fused")]
+    assert all(np.array_equal(first, v) for v in imgs.values())
+    rel = np.abs(first.astype(np.float64) - ref_img) / np.maximum(1e-3, np.abs(ref_img))
+    assert float((rel <= 1e-5).all(axis=2).mean()) >= 0.99

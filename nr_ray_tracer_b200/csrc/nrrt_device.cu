@@ -295,8 +295,8 @@ __global__ void k_encode_rgb8(const float* __restrict__ rgb, size_t n, float gam
 // fetch somebody else's ray: it waits until at least NRRT_FUSED_MIN lanes of its warp are in the same position,
 // then those lanes shade, scatter (or regenerate the next sample / fetch the next work item) and start traversing
 // their own next ray, all together.  Path state lives in shared memory (ray, throughput, running sum, hit
-// attributes: 20 doubles per thread), so neither rays nor hit records ever round-trip through HBM and there is no
-// queue, no compaction and a single launch.  Traversal and shading use the same device functions as the
+// attributes, object-space ray, time: 27 doubles per thread), so neither rays nor hit records ever round-trip
+// through HBM and there is no queue, no compaction and a single launch.  Traversal and shading use the same device functions as the
 // wavefront kernels and the same (pixel, sample-chunk) work items, so the image is bit-identical.
 #ifndef NRRT_FUSED_MIN
 #define NRRT_FUSED_MIN 16
@@ -328,7 +328,8 @@ struct SmemCtx {
 };
 
 // MB = resident blocks per SM the kernel is compiled for (register budget 65536 / (MB * 128)).  Measured on B200
-// (Cornell / spheres / teapot, Mseg/s): 3 blocks 4440 / 2957 / 791, 4 blocks 4770 / 3495 / 940.
+// (Cornell / spheres / teapot, Mseg/s, at the time): 3 blocks 4440 / 2957 / 791, 4 blocks 4770 / 3495 / 940.
+// SPEC = speculative traversal (rt_device.cuh), chosen per scene by tree size.
 template <uint32_t F, int MB, bool SPEC>
 __global__ void __launch_bounds__(NRRT_BLOCK, MB)
 k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_camera cam,

@@ -341,7 +341,7 @@ def _moving_scene(with_planes: bool):
     mats = [g.add_material(A.MAT_LAMBERTIAN, t), g.add_material(A.MAT_METAL, t, 0.2),
             g.add_material(A.MAT_DIELECTRIC, 0, 1.5), g.add_material(A.MAT_LAMBERTIAN, ck)]
     kids = []
-    for i in range(40):
+    for i in range(120 if with_planes else 40):   # 120: deep enough for the speculative-traversal instantiation
         c = rng.uniform(-4, 4, 3)
         sp = rng.uniform(-1.5, 1.5, 3) if i % 3 else np.zeros(3)   # a third of them static
         kids.append(g.add_object(A.OBJ_SPHERE, mats[i % 4], v=(*c, rng.uniform(0.2, 0.7), *sp)))
@@ -484,3 +484,42 @@ def test_large_mesh_stress(gpu_ctx):
     assert all(np.array_equal(first, v) for v in imgs.values())
     rel = np.abs(first.astype(np.float64) - ref_img) / np.maximum(1e-3, np.abs(ref_img))
     assert float((rel <= 1e-5).all(axis=2).mean()) >= 0.99
+
+
+def test_textured_sphere_field_deep_tree(gpu_ctx):
+    """150 spheres with checker / marble / noise / image-free textures: the textured-spheres kernel instantiation with
+    speculative traversal (tree of >= 64 nodes), which no shipped scene reaches."""
+    from nr_ray_tracer_b200.scene_config import CameraConfig, SceneGraph
+    g = SceneGraph()
+    rng = np.random.default_rng(9)
+    white = g.add_texture(kind=A.TEX_SOLID, color=(0.9, 0.9, 0.9))
+    dark = g.add_texture(kind=A.TEX_SOLID, color=(0.1, 0.2, 0.3))
+    texs = [g.add_texture(kind=A.TEX_CHECKER, a=white, b=dark, f0=8.0),
+            g.add_texture(kind=A.TEX_MARBLE, seed=3, octaves=7, f0=0.8),
+            g.add_texture(kind=A.TEX_NOISE, seed=5, octaves=4, f0=0.9, f1=2.0, f2=0.5), white]
+    mats = [g.add_material(A.MAT_LAMBERTIAN, t) for t in texs] + [g.add_material(A.MAT_METAL, texs[0], 0.3)]
+    kids = [g.add_object(A.OBJ_SPHERE, mats[i % len(mats)], v=(*rng.uniform(-6, 6, 3), rng.uniform(0.3, 0.8)))
+            for i in range(150)]
+    g.root = g.add_object(A.OBJ_GROUP, children=kids)
+    g.camera = CameraConfig(width=96, height=54, samples_per_pixel=8, ray_max_bounces=8, look_from=(0.0, 2.0, 16.0),
+                            look_at=(0.0, 0.0, 0.0), background_color=(0.5, 0.7, 1.0), field_of_view=45.0)
+    hs = _scene(gpu_ctx, g)
+    assert hs.desc.n_nodes >= 64
+    osc = O.OracleScene(g)
+    rays = np.concatenate([kat.aimed_rays(g, 40000), kat.random_rays(g, 40000)])
+    ref, _ = osc.trace_rays(rays)
+    for visit_all in (False, True):
+        gpu, _ = gpu_ctx.trace_rays(rays, visit_all=visit_all)
+        res = kat.compare_hits(gpu, ref)
+        assert kat.hits_ok(res) and res["hits"] > 10000, res
+    cam = api.camera_build(g.camera.to_builder_config())
+    ref_img, cnt = osc.render(O.camera_build(g.camera.to_builder_config()), seed=13)
+    imgs = []
+    for mode, mname in MODES:
+        img, st = gpu_ctx.render(cam, seed=13, mode=mode)
+        rel = np.abs(img.astype(np.float64) - ref_img) / np.maximum(1e-3, np.abs(ref_img))
+        assert float((rel <= 1e-5).all(axis=2).mean()) >= 0.99, mname
+        assert abs(st["segments"] - cnt["segments"]) <= 0.005 * cnt["segments"] + 2
+        imgs.append(img)
+    assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])
+    del hs

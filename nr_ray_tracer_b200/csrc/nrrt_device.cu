@@ -302,7 +302,9 @@ __global__ void k_encode_rgb8(const float* __restrict__ rgb, size_t n, float gam
 #define NRRT_FUSED_MIN 16
 #endif
 #define NRRT_FUSED_STATE_DOUBLES 27  // o(3) d(3) T(3) sum(3) | attr: p(3) alpha beta dobj(3) | object-space ray (6) | time
+#ifndef NRRT_FUSED_BLOCKS_PER_SM
 #define NRRT_FUSED_BLOCKS_PER_SM 4   // resident blocks the kernel is compiled for (measured: 4 beats 3 on every scene)
+#endif
 #define NRRT_FUSED_STATE_WORDS 4     // item, pixel x, pixel y, sample_end (touched only between paths)
 struct SmemCtx {
     static constexpr bool kRayInCtx = true;

@@ -32,7 +32,9 @@
 #define NRRT_F_DIELECTRIC 16u
 #define NRRT_F_MOTION 32u       // moving spheres (SphereBuilder::with_speed): rays carry Ray::time
 #define NRRT_F_ALL 63u
+#ifndef NRRT_STACK_CAP
 #define NRRT_STACK_CAP 32          // traversal stack entries per thread (host validates max_stack)
+#endif
 #define NRRT_REF_POP 0xC0000000u   // type 6: "leave instance level" marker on the stack
 #define NRRT_INF __longlong_as_double(0x7ff0000000000000LL)
 

@@ -194,6 +194,10 @@ int main(int argc, char** argv) {
             if (i + 1 >= argc) die("missing value for " + a);
             return argv[++i];
         };
+        if (a == "-h" || a == "--help") {
+            usage();
+            return 0;
+        }
         if (a == "-f" || a == "--force-overwrite") force = true;
         else if (a == "-v" || a == "--verbose") verbose = true;
         else if (a == "-o" || a == "--output") output = need();

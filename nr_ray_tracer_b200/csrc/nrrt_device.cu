@@ -1009,7 +1009,7 @@ int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
         if (sc->n_spheres && sc->sphere_speed) need |= NRRT_F_MOTION;
         ctx->features = pick_features(need);
         // speculative traversal pays once rays walk more than a handful of nodes (measured: Cornell's 17-node tree
-        // loses 9 %, the 487-node sphere field gains 7 %, the 6319-node mesh 16 %)
+        // loses 4 %, the 487-node sphere field gains 7 %, the 6319-node mesh 16 %)
         ctx->speculate = sc->n_nodes >= 64;
         if (const char* e = std::getenv("NRRT_SPECULATE")) ctx->speculate = std::atoi(e) != 0;  // developer override
     }

@@ -297,12 +297,20 @@ struct Ray32 {
     float margin;         // absolute error term that depends on the ray only
     bool degenerate;      // a zero/denormal direction component: filter disabled, exact test only
 };
-// relative error budget of one f32 slab distance: rounding of box, origin, 1/d, product (each 2^-24) + slack
-#define NRRT_BOX_EPS 4.0e-7f
+// relative error budget of one f32 slab distance: rounding of box and origin (2^-24 each), the approximate
+// reciprocal (MUFU.RCP, <= 2^-23), the products (2^-24 each) — about 5 x 2^-24 = 3e-7 — plus slack
+#define NRRT_BOX_EPS 5.0e-7f
+// 1/x for the filter only: the hardware approximation (1 instruction) instead of the IEEE-rounded reciprocal (about
+// ten); its error is part of NRRT_BOX_EPS.  Zero and denormal inputs give +-inf, which marks the ray degenerate.
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 __device__ __forceinline__ Ray32 make_ray32(d3 o, d3 d) {
     Ray32 r;
-    r.idx = __frcp_rn((float)d.x), r.idy = __frcp_rn((float)d.y), r.idz = __frcp_rn((float)d.z);
+    r.idx = rcp_fast((float)d.x), r.idy = rcp_fast((float)d.y), r.idz = rcp_fast((float)d.z);
     r.ox = (float)o.x * r.idx, r.oy = (float)o.y * r.idy, r.oz = (float)o.z * r.idz;
     float om = fmaxf(fmaxf(fabsf(r.ox), fabsf(r.oy)), fabsf(r.oz));
     r.margin = NRRT_BOX_EPS * 2.0f * om + 1e-30f;
@@ -397,7 +405,7 @@ struct MemCtx {
 // fresh ones between rounds.
 //   SPEC: speculative traversal: a lane that reaches a primitive leaf parks it and keeps walking inner nodes while
 //         other lanes of its warp are still in the node loop, instead of idling.  Pays on deep trees (teapot +16 %,
-//         sphere field +7 %), costs on tiny ones (Cornell, 17 nodes: -9 %), so the render path selects it by tree size.
+//         sphere field +7 %), costs on tiny ones (Cornell, 17 nodes: -4 %), so the render path selects it by tree size.
 template <bool VISIT_ALL, bool COUNT, uint32_t F = NRRT_F_ALL, bool SPEC = false>
 struct Traversal {
     d3 o, d;         // ray in the current space (world, or the object space of the innermost entered instance)

@@ -16,6 +16,10 @@ g = load_scene("scenes/" + name, camera_override=CameraConfig(width=1920, height
 hs = api.HostScene(g, bvh=os.environ.get("BVH", "reference"))
 ctx.upload(hs)
 cam = api.camera_build(g.camera.to_builder_config())
+if os.environ.get("WARMUP", "1") != "0":   # the first launch pays module loading (tens of ms on a cold box)
+    warm = api.camera_build(load_scene("scenes/" + name, camera_override=CameraConfig(
+        width=64, height=36, samples_per_pixel=1, ray_max_bounces=50)).camera.to_builder_config())
+    ctx.render(warm, seed=1, mode=mode)
 img, st = ctx.render(cam, seed=1, mode=mode)
 print(f"{name} spp={spp}: {st['segments']/st['device_ms']/1e3:.1f} Mseg/s device_ms={st['device_ms']:.1f} "
       f"launches={st['launches']} mean={img.mean():.6f}")

@@ -305,6 +305,7 @@ __global__ void k_encode_rgb8(const float* __restrict__ rgb, size_t n, float gam
 #ifndef NRRT_FUSED_BLOCKS_PER_SM
 #define NRRT_FUSED_BLOCKS_PER_SM 4   // resident blocks the kernel is compiled for (measured: 4 beats 3 on every scene)
 #endif
+#define NRRT_FUSED_TRIVIAL_MAX 8      // queries finished inside begin() that a lane absorbs per shading round
 #define NRRT_FUSED_STATE_WORDS 4     // item, pixel x, pixel y, sample_end (touched only between paths)
 struct SmemCtx {
     static constexpr bool kRayInCtx = true;
@@ -435,6 +436,35 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
             if (fresh && state == TRAVERSING) {
                 tr.begin(S, ctx, 0.001, NRRT_INF, nullptr);
                 ++segs;
+                // A query that is over the moment it begins (the ray misses the scene's root box — every other camera
+                // ray of an object in front of a background) is accounted for on the spot and the lane starts its next
+                // sample, instead of spending a traversal round and a shading round on a miss.  Only in the deep-tree
+                // instantiations: the extra code costs the small-scene kernels 7-12 % even when it never runs.
+                for (int rep = 0; SPEC && tr.cur == NRRT_REF_NONE && rep < NRRT_FUSED_TRIVIAL_MAX; ++rep) {
+                    const d3 T = mk3(st[6 * NRRT_BLOCK], st[7 * NRRT_BLOCK], st[8 * NRRT_BLOCK]);
+                    const d3 sum = add3(mk3(st[9 * NRRT_BLOCK], st[10 * NRRT_BLOCK], st[11 * NRRT_BLOCK]),
+                                        mul3(T, ld3(cam.background)));  // camera.rs:298
+                    ++smp.sample;
+                    if (smp.sample >= s_end) {  // item finished: publish; the next shading round fetches another
+                        size_t pb = (size_t)s_item * 3;
+                        partials[pb] = sum.x, partials[pb + 1] = sum.y, partials[pb + 2] = sum.z;
+                        s_item = (uint32_t)atomicAdd(&counters[5], 1ull);
+                        state = NEED_ITEM;
+                        break;
+                    }
+                    st[9 * NRRT_BLOCK] = sum.x, st[10 * NRRT_BLOCK] = sum.y, st[11 * NRRT_BLOCK] = sum.z;
+                    d3 o, d;
+                    double tm;
+                    camera_ray<(F & NRRT_F_MOTION) != 0>(cam, s_px, s_py, smp, o, d, tm);
+                    if (F & NRRT_F_MOTION) st[26 * NRRT_BLOCK] = tm;
+                    st[0] = o.x, st[NRRT_BLOCK] = o.y, st[2 * NRRT_BLOCK] = o.z;
+                    st[3 * NRRT_BLOCK] = d.x, st[4 * NRRT_BLOCK] = d.y, st[5 * NRRT_BLOCK] = d.z;
+                    st[6 * NRRT_BLOCK] = 1.0, st[7 * NRRT_BLOCK] = 1.0, st[8 * NRRT_BLOCK] = 1.0;
+                    bounce = 0;
+                    ++paths;
+                    tr.begin(S, ctx, 0.001, NRRT_INF, nullptr);
+                    ++segs;
+                }
             }
         }
         // ---- one traversal round for the lanes that have a query

@@ -476,9 +476,16 @@ struct Traversal {
         pend = NRRT_REF_NONE;
         cur = S.root;
         // root of the scene: an inner node tests its own box (object.rs:102)
-        if (NRRT_REF_TYPE(cur) == NRRT_REF_NODE &&
-            !root_box_test<COUNT>(&S.root_box, r32, wo, wd, tmin, tmax, tmin32, tmax32, cnt))
-            cur = NRRT_REF_NONE;
+        if (NRRT_REF_TYPE(cur) == NRRT_REF_NODE) {
+            if (!root_box_test<COUNT>(&S.root_box, r32, wo, wd, tmin, tmax, tmin32, tmax32, cnt)) cur = NRRT_REF_NONE;
+        } else if (cur != NRRT_REF_NONE && !r32.degenerate) {
+            // a scene that is one leaf (e.g. a single wrapped mesh): the reference tests no box here (object.rs:95-97),
+            // so only what the f32 filter PROVES missed is culled — exactly as for a leaf child of an inner node
+            float e, g, m;
+            box_filter(r32, (float)S.root_box.lo[0], (float)S.root_box.lo[1], (float)S.root_box.lo[2],
+                       (float)S.root_box.hi[0], (float)S.root_box.hi[1], (float)S.root_box.hi[2], tmin32, tmax32, e, g, m);
+            if (g < -m) cur = NRRT_REF_NONE;
+        }
     }
 
     // `stack` is this thread's slice of shared memory, stride `sstride` (bank-conflict free).

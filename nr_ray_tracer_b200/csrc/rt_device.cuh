@@ -774,7 +774,13 @@ __device__ __forceinline__ void resolve_hit_attr(const DevScene& S, const HitId&
 }
 
 // --------------------------------------------------------------------------- Philox4x32-10
-__device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 c) {
+#ifndef NRRT_PHILOX_INLINE
+#define NRRT_PHILOX_INLINE __forceinline__
+#endif
+#ifndef NRRT_DISK_INLINE
+#define NRRT_DISK_INLINE __forceinline__
+#endif
+__device__ NRRT_PHILOX_INLINE uint4 philox4x32_10(uint2 key, uint4 c) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
@@ -807,7 +813,7 @@ __device__ __forceinline__ d3 random_in_unit_sphere(const Sampler& s, uint32_t s
     }
 }
 // vector.rs:72-81 — p/|p|^2, |p|^2 < 1
-__device__ __forceinline__ d3 random_in_unit_disk(const Sampler& s) {
+__device__ NRRT_DISK_INLINE d3 random_in_unit_disk(const Sampler& s) {
     for (uint32_t it = 1;; ++it) {
         uint4 r = s.draw(0, it);
         d3 p = mk3(u_m1_1(r.x), u_m1_1(r.y), 0.0);

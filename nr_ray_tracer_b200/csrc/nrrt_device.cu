@@ -353,7 +353,7 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
     uint32_t segs = 0, paths = 0;  // per-thread; a thread traces far fewer than 2^32 segments
 
     enum : uint32_t { NEED_ITEM = 0, NEED_PATH = 1, TRAVERSING = 2, HIT_READY = 3, RETIRED = 4 };
-    uint32_t state = NEED_ITEM;
+    uint32_t state = w < P.n_slots ? NEED_ITEM : RETIRED;  // a partial last block: the surplus threads own no item
     s_item = w;  // the first n_slots items are pre-assigned; the counter starts at n_slots
     s_px = s_py = s_end = 0;
     Sampler smp{P.key, 0u, 0u};

@@ -523,3 +523,18 @@ def test_textured_sphere_field_deep_tree(gpu_ctx):
         imgs.append(img)
     assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])
     del hs
+
+
+def test_slot_limits_do_not_change_the_result(gpu_ctx):
+    """max_slots that is not a multiple of the block size, smaller than a block, or larger than the work: every work
+    item is still rendered exactly once (same image, same segment and path counts) in every kernel design."""
+    g = load("cornell-box-scene.json", width=64, height=36, samples_per_pixel=6)
+    hs = _scene(gpu_ctx, g)
+    cam = api.camera_build(g.camera.to_builder_config())
+    ref_img, ref_st = gpu_ctx.render(cam, seed=3)
+    for mode, mname in MODES:
+        for slots in (1, 100, 1000, 4097, 1 << 22):
+            img, st = gpu_ctx.render(cam, seed=3, mode=mode, max_slots=slots)
+            assert np.array_equal(img, ref_img), (mname, slots)
+            assert (st["segments"], st["paths"]) == (ref_st["segments"], ref_st["paths"]), (mname, slots)
+    del hs

@@ -294,8 +294,10 @@ __device__ __noinline__ bool tie_candidate_wins(const DevScene& S, uint32_t cand
 struct Ray32 {
     float idx, idy, idz;  // 1/d
     float ox, oy, oz;     // o/d
-    float margin;         // absolute error term that depends on the ray only
-    bool degenerate;      // a zero/denormal direction component: filter disabled, exact test only
+    float margin;         // absolute error term that depends on the ray only; +inf for a degenerate ray (a zero /
+                          // denormal / overflowing direction component): then no filter comparison is ever
+                          // conclusive — every child is visited, every inner box goes to the exact test, nothing is
+                          // pruned — without a flag to test in the node loop
 };
 // relative error budget of one f32 slab distance: rounding of box and origin (2^-24 each), the approximate
 // reciprocal (MUFU.RCP, <= 2^-23), the products (2^-24 each) — about 5 x 2^-24 = 3e-7 — plus slack
@@ -315,7 +317,7 @@ __device__ __forceinline__ Ray32 make_ray32(d3 o, d3 d) {
     float om = fmaxf(fmaxf(fabsf(r.ox), fabsf(r.oy)), fabsf(r.oz));
     r.margin = NRRT_BOX_EPS * 2.0f * om + 1e-30f;
     float s = (r.idx + r.idy + r.idz) + (r.ox + r.oy + r.oz);  // inf or nan if any term is
-    r.degenerate = !(fabsf(s) < 3.0e38f) || !(om < 3.0e38f);
+    if (!(fabsf(s) < 3.0e38f) || !(om < 3.0e38f)) r.margin = __int_as_float(0x7f800000);
     return r;
 }
 
@@ -338,7 +340,7 @@ __device__ __forceinline__ void box_filter(const Ray32& r, float lx, float ly, f
 template <bool COUNT>
 __device__ __forceinline__ bool root_box_test(const nrrt_box* b, const Ray32& r32, d3 o, d3 d, double tmin,
                                               double tmax, float tmin32, float tmax32, TraceCounters* cnt) {
-    if (!r32.degenerate) {
+    {
         float e, g, m;
         box_filter(r32, (float)b->lo[0], (float)b->lo[1], (float)b->lo[2], (float)b->hi[0], (float)b->hi[1],
                    (float)b->hi[2], tmin32, tmax32, e, g, m);
@@ -478,7 +480,7 @@ struct Traversal {
         // root of the scene: an inner node tests its own box (object.rs:102)
         if (NRRT_REF_TYPE(cur) == NRRT_REF_NODE) {
             if (!root_box_test<COUNT>(&S.root_box, r32, wo, wd, tmin, tmax, tmin32, tmax32, cnt)) cur = NRRT_REF_NONE;
-        } else if (cur != NRRT_REF_NONE && !r32.degenerate) {
+        } else if (cur != NRRT_REF_NONE) {
             // a scene that is one leaf (e.g. a single wrapped mesh): the reference tests no box here (object.rs:95-97),
             // so only what the f32 filter PROVES missed is culled — exactly as for a leaf child of an inner node
             float e, g, m;
@@ -517,10 +519,10 @@ struct Traversal {
             box_filter(r32, n0.w, n1.x, n1.y, n2.y, n2.z, n2.w, tmin32, tmax32, e1, g1, m1);
             // leaves are not box-tested by the reference (object.rs:95-97): visit unless certainly missed;
             // inner children must pass the reference's test: certain from the filter, else exact
-            bool v0 = (c0 != NRRT_REF_NONE) && (r32.degenerate || !(g0 < -m0));
-            bool v1 = (c1 != NRRT_REF_NONE) && (r32.degenerate || !(g1 < -m1));
-            bool amb0 = v0 && NRRT_REF_TYPE(c0) == NRRT_REF_NODE && (r32.degenerate || !(g0 >= m0));
-            bool amb1 = v1 && NRRT_REF_TYPE(c1) == NRRT_REF_NODE && (r32.degenerate || !(g1 >= m1));
+            bool v0 = (c0 != NRRT_REF_NONE) && !(g0 < -m0);
+            bool v1 = (c1 != NRRT_REF_NONE) && !(g1 < -m1);
+            bool amb0 = v0 && NRRT_REF_TYPE(c0) == NRRT_REF_NODE && !(g0 >= m0);
+            bool amb1 = v1 && NRRT_REF_TYPE(c1) == NRRT_REF_NODE && !(g1 >= m1);
             if (amb0 || amb1) {  // rare
                 d3 o, d;
                 load_ray(ctx, o, d);
@@ -533,7 +535,7 @@ struct Traversal {
                     v1 = box_hit_exact(S.child_boxes + 2 * (size_t)ni + 1, o, d, tmin, tmax);
                 }
             }
-            if (!VISIT_ALL && !r32.degenerate) {
+            if (!VISIT_ALL) {
                 // prune children that start certainly behind the best hit (ties are kept: margin > 0)
                 v0 = v0 && !(e0 - m0 > tcull);
                 v1 = v1 && !(e1 - m1 > tcull);

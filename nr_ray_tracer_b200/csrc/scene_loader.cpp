@@ -58,6 +58,32 @@ struct Value {
 };
 
 // ---------------------------------------------------------------------------------------------- JSON
+// Number grammar shared by the two parsers (serde_json and the toml crate are strict about it): an optional sign
+// ('-' only in JSON), an integer part without leading zeros, an optional fraction with at least one digit, an optional
+// exponent with at least one digit.  TOML additionally allows '+' and '_' between digits (already removed here).
+static bool strict_number(const std::string& t, bool toml) {
+    size_t i = 0, n = t.size();
+    if (i < n && (t[i] == '-' || (toml && t[i] == '+'))) ++i;
+    if (i >= n || !isdigit((unsigned char)t[i])) return false;
+    if (t[i] == '0') {
+        ++i;
+    } else {
+        while (i < n && isdigit((unsigned char)t[i])) ++i;
+    }
+    if (i < n && t[i] == '.') {
+        ++i;
+        if (i >= n || !isdigit((unsigned char)t[i])) return false;
+        while (i < n && isdigit((unsigned char)t[i])) ++i;
+    }
+    if (i < n && (t[i] == 'e' || t[i] == 'E')) {
+        ++i;
+        if (i < n && (t[i] == '-' || t[i] == '+')) ++i;
+        if (i >= n || !isdigit((unsigned char)t[i])) return false;
+        while (i < n && isdigit((unsigned char)t[i])) ++i;
+    }
+    return i == n;
+}
+
 class Json {
   public:
     explicit Json(const std::string& t) : s_(t) {}
@@ -113,6 +139,7 @@ class Json {
         }
         if (p_ == st) err("value expected");
         std::string t = s_.substr(st, p_ - st);
+        if (!strict_number(t, false)) err("bad number '" + t + "'");
         auto v = Value::make(is_float ? Value::Float : Value::Int);
         char* e = nullptr;
         if (is_float) {
@@ -128,6 +155,7 @@ class Json {
         std::string out;
         while (p_ < s_.size() && s_[p_] != '"') {
             char c = s_[p_++];
+            if ((unsigned char)c < 0x20) err("control character in string");
             if (c == '\\') {
                 if (p_ >= s_.size()) err("bad escape");
                 char e = s_[p_++];
@@ -137,6 +165,9 @@ class Json {
                     case 'r': out += '\r'; break;
                     case 'b': out += '\b'; break;
                     case 'f': out += '\f'; break;
+                    case '"': out += '"'; break;
+                    case '\\': out += '\\'; break;
+                    case '/': out += '/'; break;
                     case 'u': {
                         if (p_ + 4 > s_.size()) err("bad \\u escape");
                         unsigned cp = (unsigned)std::strtoul(s_.substr(p_, 4).c_str(), nullptr, 16);
@@ -146,7 +177,7 @@ class Json {
                         else { out += (char)(0xE0 | (cp >> 12)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
                         break;
                     }
-                    default: out += e;
+                    default: err("bad escape");
                 }
             } else {
                 out += c;
@@ -222,6 +253,9 @@ class Toml {
             if (p_ >= s_.size()) break;
             if (s_[p_] == '[') {
                 header();
+                skip_ws();
+                if (p_ < s_.size() && s_[p_] == '#') skip_comment();
+                if (p_ < s_.size() && s_[p_] != '\n' && s_[p_] != '\r') err("newline expected after table header");
             } else {
                 keyval(cur_);
                 skip_ws();
@@ -342,7 +376,7 @@ class Toml {
         std::string out;
         while (p_ < s_.size() && s_[p_] != '"') {
             char c = s_[p_++];
-            if (c == '\n') err("newline in string");
+            if ((unsigned char)c < 0x20 && c != '\t') err("control character in string");
             if (c == '\\') {
                 if (p_ >= s_.size()) err("bad escape");
                 char e = s_[p_++];
@@ -416,9 +450,9 @@ class Toml {
                 return v;
             }
             for (;;) {
-                skip_ws_nl();  // lenient: the reference's files break inline tables across lines inside arrays
+                skip_ws();  // TOML 1.0 (what the toml crate implements): no newline inside an inline table
                 keyval(v);
-                skip_ws_nl();
+                skip_ws();
                 if (p_ < s_.size() && s_[p_] == ',') {
                     ++p_;
                     continue;
@@ -454,6 +488,7 @@ class Toml {
             v->f = bare == "inf" ? (t[0] == '-' ? -INFINITY : INFINITY) : NAN;
             return v;
         }
+        if (!strict_number(t, true)) err("bad value '" + t + "'");
         bool is_float = t.find_first_of(".eE") != std::string::npos;
         auto v = Value::make(is_float ? Value::Float : Value::Int);
         char* e = nullptr;

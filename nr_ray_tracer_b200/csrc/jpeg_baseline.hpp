@@ -281,7 +281,7 @@ class Decoder {
             int d[8];
             for (int r = 0; r < 8; ++r) d[r] = in[r * 8 + col] * (int)q[r * 8 + col];
             if (!(d[1] | d[2] | d[3] | d[4] | d[5] | d[6] | d[7])) {
-                int dc = d[0] << 2;
+                int dc = d[0] * 4;  // multiplications, not shifts: the operands may be negative
                 for (int r = 0; r < 8; ++r) ws[r * 8 + col] = dc;
                 continue;
             }
@@ -289,7 +289,7 @@ class Decoder {
             int64_t z1 = (z2 + z3) * C0_541;
             int64_t tmp2 = z1 + z3 * (-C1_847), tmp3 = z1 + z2 * C0_765;
             z2 = d[0], z3 = d[4];
-            int64_t tmp0 = (z2 + z3) << 13, tmp1 = (z2 - z3) << 13;
+            int64_t tmp0 = (z2 + z3) * 8192, tmp1 = (z2 - z3) * 8192;
             int64_t tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
             tmp0 = d[7], tmp1 = d[5], tmp2 = d[3], tmp3 = d[1];
             z1 = tmp0 + tmp3, z2 = tmp1 + tmp2, z3 = tmp0 + tmp2;
@@ -313,7 +313,7 @@ class Decoder {
             int64_t z2 = w[2], z3 = w[6];
             int64_t z1 = (z2 + z3) * C0_541;
             int64_t tmp2 = z1 + z3 * (-C1_847), tmp3 = z1 + z2 * C0_765;
-            int64_t tmp0 = ((int64_t)w[0] + w[4]) << 13, tmp1 = ((int64_t)w[0] - w[4]) << 13;
+            int64_t tmp0 = ((int64_t)w[0] + w[4]) * 8192, tmp1 = ((int64_t)w[0] - w[4]) * 8192;
             int64_t tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
             tmp0 = w[7], tmp1 = w[5], tmp2 = w[3], tmp3 = w[1];
             z1 = tmp0 + tmp3, z2 = tmp1 + tmp2, z3 = tmp0 + tmp2;

@@ -316,8 +316,9 @@ struct Flattener {
         for (int a = 0; a < 3; ++a) finite = finite && std::isfinite(cbox.lo[a]) && std::isfinite(cbox.hi[a]);
         bool median = n <= 2 || ceil_log2(n) + 1 >= depth_left || !finite || !(cbox.hi[axis] - cbox.lo[axis] > 0.0);
         constexpr int NB = 16;
-        auto bin_of = [&](const Emitted& e, int a) {
-            return std::min(NB - 1, (int)((centroid(e, a) - cbox.lo[a]) / (cbox.hi[a] - cbox.lo[a]) * NB));
+        auto bin_of = [&](const Emitted& e, int a) {  // NaN / out-of-range centroids (malformed input) land in bin 0
+            const double x = (centroid(e, a) - cbox.lo[a]) / (cbox.hi[a] - cbox.lo[a]) * NB;
+            return (x >= 0.0 && x < (double)NB) ? (int)x : (x >= (double)NB ? NB - 1 : 0);
         };
         if (!median) {
             double best_cost = std::numeric_limits<double>::infinity();

@@ -239,3 +239,29 @@ def test_sah_surface_area_cost_is_lower_than_median_split_on_the_mesh():
         area = ext[..., 0] * ext[..., 1] + ext[..., 1] * ext[..., 2] + ext[..., 2] * ext[..., 0]
         return float(area.sum())                   # sum of child-box areas ~ expected node + leaf visits
     assert sah_cost(api.HostScene(g, bvh="sah")) < 0.8 * sah_cost(api.HostScene(g))
+
+
+def test_non_finite_geometry_does_not_break_either_build():
+    """NaN / inf coordinates (malformed input): both tree builds terminate with a valid flat scene (the reference
+    sorts with total_cmp; the SAH binning must not index out of range)."""
+    from nr_ray_tracer_b200 import api
+    from nr_ray_tracer_b200.scene_config import SceneGraph
+    g = SceneGraph()
+    t = g.add_texture(kind=A.TEX_SOLID, color=(1, 1, 1))
+    m = g.add_material(A.MAT_LAMBERTIAN, t)
+    rng = np.random.default_rng(0)
+    kids = []
+    for i in range(300):
+        c = rng.uniform(-5, 5, 3)
+        if i % 37 == 0:
+            c[0] = float("nan")
+        if i % 53 == 0:
+            c[1] = float("inf")
+        kids.append(g.add_object(A.OBJ_SPHERE, m, v=(*c, 0.3)))
+    g.root = g.add_object(A.OBJ_GROUP, children=kids)
+    for bvh in ("reference", "sah"):
+        hs = api.HostScene(g, bvh=bvh)
+        assert hs.desc.n_nodes == 299 and hs.desc.n_spheres == 300 and hs.desc.max_stack <= 32
+        refs = hs.nodes()["child"].reshape(-1)
+        leaves = refs[(refs >> A.REF_TYPE_SHIFT) != A.REF_NODE]
+        assert len(set(leaves.tolist())) == 300

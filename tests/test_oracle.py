@@ -219,6 +219,68 @@ def test_closed_white_sphere_leaks_because_scatter_is_not_a_unit_offset():
     assert np.allclose(img * 16, np.round(img * 16), atol=1e-5) and 0.3 < img.mean() < 1.0
 
 
+def _two_material_scene(first_kind, first_param, first_color, light_quad, light_color=(1.0, 1.0, 1.0), intensity=4.0):
+    """A big quad in the plane y = 0 with the material under test, and one small light quad."""
+    g = SceneGraph()
+    t0 = g.add_texture(kind=A.TEX_SOLID, color=first_color)
+    m0 = g.add_material(first_kind, t0, first_param)
+    t1 = g.add_texture(kind=A.TEX_SOLID, color=light_color)
+    m1 = g.add_material(A.MAT_DIFFUSE_LIGHT, t1, intensity)
+    floor = g.add_object(A.OBJ_QUAD, m0, v=(-5, 0, -5, 0, 0, 10, 10, 0, 0))   # u x v = +y: the front face looks up
+    light = g.add_object(A.OBJ_QUAD, m1, v=light_quad)
+    g.root = g.add_object(A.OBJ_GROUP, children=[floor, light])
+    return g
+
+
+def test_metal_without_fuzz_is_a_perfect_mirror():
+    """metal.rs:73-91: scattered = reflect(dir, n).normalize() + fuzz * random_in_unit_sphere; colour = texture.
+    A ray coming down at 45 degrees onto the plane y = 0 leaves along (1, 1, 0) and meets a light placed exactly
+    there; seen through a bounce the light counts with its intensity (diffuse_light.rs:63-75)."""
+    light_at = lambda cx, cy: (cx - 0.35, cy + 0.35, -0.5, 0.7, -0.7, 0.0, 0.0, 0.0, 1.0)   # noqa: E731 — faces the origin
+    cam = dict(width=1, height=1, samples_per_pixel=1, ray_max_bounces=5, look_from=(-2.0, 2.0, 0.0),
+               look_at=(0.0, 0.0, 0.0), field_of_view=1.0, background_color=(0.0, 0.0, 0.0))
+    g = _two_material_scene(A.MAT_METAL, 0.0, (0.8, 0.6, 0.2), light_at(2.0, 2.0))
+    img, cnt = _render_const(g, **cam)
+    assert np.allclose(img[0, 0], [0.8 * 4.0, 0.6 * 4.0, 0.2 * 4.0], rtol=1e-6) and cnt["segments"] == 2
+    # the same light one unit off the mirror direction is not seen: the path ends on the (black) background
+    g = _two_material_scene(A.MAT_METAL, 0.0, (0.8, 0.6, 0.2), light_at(3.2, 0.8))
+    img, cnt = _render_const(g, **cam)
+    assert (img == 0).all() and cnt["segments"] == 2
+    # with fuzz the direction is perturbed by fuzz * p/|p|^2 (|p/|p|^2| >= 1): at fuzz 0.2 the 0.7-wide light two
+    # units away is still hit by some samples but no longer by all
+    g = _two_material_scene(A.MAT_METAL, 0.2, (1.0, 1.0, 1.0), light_at(2.0, 2.0))
+    img, cnt = _render_const(g, **dict(cam, samples_per_pixel=400, field_of_view=0.01))
+    assert 0.05 * 4.0 < img[0, 0, 0] < 0.95 * 4.0
+
+
+def test_dielectric_follows_snell_and_schlick():
+    """dielectric.rs:39-67.  45 degrees onto glass (index 1.5) from outside: ri = 1/1.5, sin(t) = sin(45)/1.5, the
+    refracted ray leaves the origin along (sin t, -cos t, 0); reflectance (Schlick, :13-19) r0 = ((1-ri)/(1+ri))^2
+    = 0.04, R = r0 + (1-r0)(1-cos 45)^5 = 0.04207; the ray reflects iff R > u for one uniform draw."""
+    sin_t = math.sin(math.radians(45.0)) / 1.5
+    cos_t = math.sqrt(1.0 - sin_t * sin_t)
+    x_hit = 2.0 * sin_t / cos_t                                   # where the refracted ray crosses y = -2
+    light_below = lambda cx: (cx - 0.2, -2.0, -0.2, 0.4, 0.0, 0.0, 0.0, 0.0, 0.4)   # noqa: E731
+    R = 0.04 + 0.96 * (1.0 - math.cos(math.radians(45.0))) ** 5
+    cam = dict(width=1, height=1, samples_per_pixel=4000, ray_max_bounces=5, look_from=(-2.0, 2.0, 0.0),
+               look_at=(0.0, 0.0, 0.0), field_of_view=0.01, background_color=(0.0, 0.0, 0.0))
+    g = _two_material_scene(A.MAT_DIELECTRIC, 1.5, (1.0, 1.0, 1.0), light_below(x_hit), intensity=1.0)
+    img, cnt = _render_const(g, **cam)
+    refracted = float(img[0, 0, 0])          # attenuation 1 (:61), light 1: the pixel is the refracted fraction
+    assert abs(refracted - (1.0 - R)) < 4.0 * math.sqrt(R * (1.0 - R) / 4000.0) + 1e-3
+    assert cnt["segments"] == 2 * cnt["paths"]
+    # a light where a straight (unrefracted) continuation would land, x = 2 at y = -2, stays dark
+    g = _two_material_scene(A.MAT_DIELECTRIC, 1.5, (1.0, 1.0, 1.0), light_below(2.0), intensity=1.0)
+    img, _ = _render_const(g, **cam)
+    assert float(img[0, 0, 0]) == 0.0
+    # from inside the glass beyond the critical angle (asin(1/1.5) = 41.8 deg) everything reflects: the ray comes
+    # up at 45 degrees against the underside and is mirrored back down onto a light below
+    cam_in = dict(cam, look_from=(-2.0, -2.0, 0.0), samples_per_pixel=200)
+    g = _two_material_scene(A.MAT_DIELECTRIC, 1.5, (1.0, 1.0, 1.0), light_below(2.0), intensity=1.0)
+    img, _ = _render_const(g, **cam_in)
+    assert abs(float(img[0, 0, 0]) - 1.0) < 1e-6
+
+
 # ---------------------------------------------------------------- golden fixtures (pin the oracle)
 @pytest.mark.parametrize("name", GOLDEN_SCENES + ["_textures"])
 def test_oracle_reproduces_golden(name):

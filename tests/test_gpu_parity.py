@@ -538,3 +538,36 @@ def test_slot_limits_do_not_change_the_result(gpu_ctx):
             assert np.array_equal(img, ref_img), (mname, slots)
             assert (st["segments"], st["paths"]) == (ref_st["segments"], ref_st["paths"]), (mname, slots)
     del hs
+
+
+def test_hand_derived_material_cases_on_the_gpu(gpu_ctx):
+    """The hand-derived cases that pin the oracle (tests/test_oracle.py), straight against the CUDA path: a fuzz-free
+    metal is an exact mirror (metal.rs:73-91); a dielectric refracts by Snell's law with Schlick's reflectance and
+    reflects totally from inside beyond the critical angle (dielectric.rs:13-19, 39-67)."""
+    import math
+    from tests.test_oracle import _two_material_scene
+
+    def render(g, mode, **cam):
+        for k, v in cam.items():
+            setattr(g.camera, k, v)
+        hs = _scene(gpu_ctx, g)
+        img, st = gpu_ctx.render(api.camera_build(g.camera.to_builder_config()), seed=1, mode=mode)
+        del hs
+        return img, st
+
+    cam = dict(width=1, height=1, samples_per_pixel=1, ray_max_bounces=5, look_from=(-2.0, 2.0, 0.0),
+               look_at=(0.0, 0.0, 0.0), field_of_view=1.0, background_color=(0.0, 0.0, 0.0))
+    sin_t = math.sin(math.radians(45.0)) / 1.5
+    x_hit = 2.0 * sin_t / math.sqrt(1.0 - sin_t * sin_t)
+    R = 0.04 + 0.96 * (1.0 - math.cos(math.radians(45.0))) ** 5
+    for mode, mname in MODES:
+        g = _two_material_scene(A.MAT_METAL, 0.0, (0.8, 0.6, 0.2), (2.0 - 0.35, 2.0 + 0.35, -0.5, 0.7, -0.7, 0, 0, 0, 1.0))
+        img, st = render(g, mode, **cam)
+        assert np.allclose(img[0, 0], [3.2, 2.4, 0.8], rtol=1e-6) and st["segments"] == 2, mname
+        glass = dict(cam, samples_per_pixel=4000, field_of_view=0.01)
+        g = _two_material_scene(A.MAT_DIELECTRIC, 1.5, (1, 1, 1), (x_hit - 0.2, -2.0, -0.2, 0.4, 0, 0, 0, 0, 0.4), intensity=1.0)
+        img, st = render(g, mode, **glass)
+        assert abs(float(img[0, 0, 0]) - (1.0 - R)) < 4.0 * math.sqrt(R * (1.0 - R) / 4000.0) + 1e-3, mname
+        g = _two_material_scene(A.MAT_DIELECTRIC, 1.5, (1, 1, 1), (2.0 - 0.2, -2.0, -0.2, 0.4, 0, 0, 0, 0, 0.4), intensity=1.0)
+        img, st = render(g, mode, **dict(glass, look_from=(-2.0, -2.0, 0.0), samples_per_pixel=200))
+        assert abs(float(img[0, 0, 0]) - 1.0) < 1e-6, mname

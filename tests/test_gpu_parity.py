@@ -545,7 +545,7 @@ def test_hand_derived_material_cases_on_the_gpu(gpu_ctx):
     metal is an exact mirror (metal.rs:73-91); a dielectric refracts by Snell's law with Schlick's reflectance and
     reflects totally from inside beyond the critical angle (dielectric.rs:13-19, 39-67)."""
     import math
-    from tests.test_oracle import _two_material_scene
+    from tests.test_oracle import _lambertian_leak_scene, _two_material_scene
 
     def render(g, mode, **cam):
         for k, v in cam.items():
@@ -571,3 +571,7 @@ def test_hand_derived_material_cases_on_the_gpu(gpu_ctx):
         g = _two_material_scene(A.MAT_DIELECTRIC, 1.5, (1, 1, 1), (2.0 - 0.2, -2.0, -0.2, 0.4, 0, 0, 0, 0, 0.4), intensity=1.0)
         img, st = render(g, mode, **dict(glass, look_from=(-2.0, -2.0, 0.0), samples_per_pixel=200))
         assert abs(float(img[0, 0, 0]) - 1.0) < 1e-6, mname
+        # quirk Q1 (vector.rs:61-70): a Lambertian scatter dives through its own surface with probability 1/8
+        img, st = render(_lambertian_leak_scene(), mode, **dict(cam, samples_per_pixel=20000, ray_max_bounces=2,
+                                                              field_of_view=0.01))
+        assert abs(float(img[0, 0, 0]) / (0.5 * 2.0) - 0.125) < 4.0 * math.sqrt(0.125 * 0.875 / 20000), mname

@@ -281,6 +281,27 @@ def test_dielectric_follows_snell_and_schlick():
     assert abs(float(img[0, 0, 0]) - 1.0) < 1e-6
 
 
+def _lambertian_leak_scene():
+    """A Lambertian floor (front face up) over a huge light: only scattered rays that go THROUGH the floor see it."""
+    g = _two_material_scene(A.MAT_LAMBERTIAN, 0.0, (0.5, 0.5, 0.5), (-500.0, -1.0, -500.0, 1000.0, 0, 0, 0, 0, 1000.0),
+                            intensity=2.0)
+    return g
+
+
+def test_lambertian_scatter_is_normal_plus_p_over_p_squared():
+    """lambertian.rs:39-55 + vector.rs:61-70 (quirk Q1): the scatter direction is n + p/|p|^2 with p uniform in the
+    unit ball, so |offset| = 1/|p| >= 1 and the ray dives below the surface iff cos(theta) < -|p|:
+    P = int_0^1 3r^2 (1-r)/2 dr = 1/8.  (The textbook n + unit vector never goes below.)  With a light under the floor
+    and a black sky the pixel is albedo * emission * 1/8."""
+    g = _lambertian_leak_scene()
+    n = 20000
+    img, cnt = _render_const(g, width=1, height=1, samples_per_pixel=n, ray_max_bounces=2, look_from=(-2.0, 2.0, 0.0),
+                             look_at=(0.0, 0.0, 0.0), field_of_view=0.01, background_color=(0.0, 0.0, 0.0))
+    p = float(img[0, 0, 0]) / (0.5 * 2.0)
+    assert abs(p - 0.125) < 4.0 * math.sqrt(0.125 * 0.875 / n)
+    assert cnt["segments"] == 2 * cnt["paths"]
+
+
 # ---------------------------------------------------------------- golden fixtures (pin the oracle)
 @pytest.mark.parametrize("name", GOLDEN_SCENES + ["_textures"])
 def test_oracle_reproduces_golden(name):

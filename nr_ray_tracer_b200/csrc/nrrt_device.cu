@@ -17,6 +17,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <chrono>
 #include <vector>
 
 #include "rt_device.cuh"
@@ -765,6 +767,7 @@ struct nrrt_ctx {
     uint32_t features = NRRT_F_ALL;    // NRRT_F_* mask of the uploaded scene
     double trace_time = 0.0;           // Ray::time of nrrt_trace_rays queries
     bool speculate = false;            // fused kernel: speculative traversal (deep trees only)
+    cudaStream_t side = nullptr;       // progress polling while a single-launch render runs (created on first use)
 };
 
 #define CK(call)                                                                                   \
@@ -872,6 +875,7 @@ void nrrt_destroy(nrrt_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_count) cudaFreeHost(ctx->h_count);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1403,6 +1407,25 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         ++launches;
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (progress && !wavefront && n != 0 && c.ray_max_bounces != 0) {
+        // (before the image copy below: a copy into pageable host memory blocks until the render is done)
+        // The single-launch kernels hand work items out from a device counter: read it from a side stream while the
+        // render runs and report the pixels whose items have all been handed out (render.rs:48-59 ticks once per pixel).
+        if (!ctx->side) CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+        unsigned long long* h_next = reinterpret_cast<unsigned long long*>(ctx->h_count);  // pinned
+        uint64_t last = 0;
+        while (cudaEventQuery(ctx->ev1) == cudaErrorNotReady) {
+            CK(cudaMemcpyAsync(h_next, ctx->d_counters + 5, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->side));
+            CK(cudaStreamSynchronize(ctx->side));
+            const uint64_t handed = *h_next > P.n_slots ? *h_next - P.n_slots : 0;  // the last n_slots are still in flight
+            const uint64_t done = std::min<uint64_t>(handed, P.n_items) * P.n_owned_pixels / std::max<uint32_t>(P.n_items, 1u);
+            if (done > last && done < P.n_owned_pixels) {
+                progress(done, P.n_owned_pixels, user);
+                last = done;
+            }
+            std::this_thread::sleep_for(std::chrono::milliseconds(20));
+        }
+    }
     if (!out_dev) {
         // copy only the owned rows back into the caller's full-size buffer
         const uint32_t R = o.rows_per_block;

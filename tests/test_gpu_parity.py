@@ -575,3 +575,22 @@ def test_hand_derived_material_cases_on_the_gpu(gpu_ctx):
         img, st = render(_lambertian_leak_scene(), mode, **dict(cam, samples_per_pixel=20000, ray_max_bounces=2,
                                                               field_of_view=0.01))
         assert abs(float(img[0, 0, 0]) / (0.5 * 2.0) - 0.125) < 4.0 * math.sqrt(0.125 * 0.875 / 20000), mname
+
+
+def test_progress_is_reported_while_a_single_launch_render_runs(gpu_ctx):
+    """render.rs:48-59 ticks a progress bar once per pixel; the fused kernel is one launch, so the host polls the
+    device-side work counter from a side stream and reports the pixels handed out so far."""
+    g = load("cornell-box-scene.json", width=1280, height=720, samples_per_pixel=128)
+    hs = _scene(gpu_ctx, g)
+    cam = api.camera_build(g.camera.to_builder_config())
+    ref, _ = gpu_ctx.render(cam, seed=2)
+    for mode in (A.MODE_FUSED, A.MODE_MEGAKERNEL):
+        calls = []
+        img, _ = gpu_ctx.render(cam, seed=2, mode=mode, progress=lambda done, total: calls.append((done, total)))
+        assert np.array_equal(img, ref)
+        total = 1280 * 720
+        assert calls and calls[-1] == (total, total) and all(t == total for _, t in calls)
+        done = [d for d, _ in calls]
+        assert done == sorted(done) and len(set(done)) == len(done)
+        assert len(calls) >= 3, calls          # at least two intermediate reports in a ~0.15 s render
+    del hs

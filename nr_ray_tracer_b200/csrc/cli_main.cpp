@@ -250,7 +250,13 @@ int main(int argc, char** argv) {
     opts.mode = mode == "megakernel" ? NRRT_MODE_MEGAKERNEL : (mode == "wavefront" ? NRRT_MODE_WAVEFRONT : NRRT_MODE_FUSED);
     nrrt_render_stats st;
     auto t0 = std::chrono::steady_clock::now();
-    if (nrrt_render(ctx, &cam, &opts, image.data(), nullptr, nullptr, &st) != NRRT_OK) die(nrrt_last_error(ctx));
+    // the reference draws a per-pixel progress bar (render.rs:48-59); with -v a percentage goes to stderr
+    nrrt_progress_fn on_progress = [](uint64_t done, uint64_t total, void*) {
+        std::fprintf(stderr, "\rrendering: %3u%%", total ? (unsigned)(done * 100 / total) : 100u);
+        if (done >= total) std::fputc('\n', stderr);
+    };
+    if (nrrt_render(ctx, &cam, &opts, image.data(), verbose ? on_progress : nullptr, nullptr, &st) != NRRT_OK)
+        die(nrrt_last_error(ctx));
     auto t1 = std::chrono::steady_clock::now();
     std::vector<uint8_t> rgb8(image.size());
     if (nrrt_encode_rgb8(ctx, image.data(), cam.width, cam.height, gamma, 0, rgb8.data()) != NRRT_OK) die(nrrt_last_error(ctx));

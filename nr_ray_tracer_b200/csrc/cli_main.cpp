@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+#include <unistd.h>
+
 #include "../../include/nrrt.h"
 
 static void die(const std::string& m) {
@@ -112,6 +114,7 @@ static void write_ppm(FILE* f, const uint8_t* rgb, uint32_t w, uint32_t h) {
 static void usage() {
     std::puts(
         "Usage: nr-ray-tracer render [OPTIONS] <SCENE>\n"
+        "       nr-ray-tracer create <cornell-box|cube|earth|noise|quads|triangles|spheres|simple-lights|convert-stl> [-o FILE] ...\n"
         "  -o, --output <FILE>            output file (.png or .ppm) [default: out.png]\n"
         "  -f, --force-overwrite          overwrite the output file\n"
         "      --gamma-value <G>          gamma [default: 0.5]\n"
@@ -125,12 +128,42 @@ static void usage() {
         "Every camera option falls back to NR_RT_CAMERA_<NAME> (e.g. NR_RT_CAMERA_SAMPLES_PER_PIXEL).");
 }
 
+// `nr-ray-tracer create <kind> ...` (commands/create/*.rs): the scene generators are host-side authoring tools and
+// live in the Python package (nr_ray_tracer_b200/create.py); this command hands its arguments over to them so the
+// binary keeps the reference's two subcommands.  The package is found relative to the binary (bin/ -> package -> repo).
+static int run_create(int argc, char** argv) {
+    char self[4096];
+    ssize_t n = readlink("/proc/self/exe", self, sizeof self - 1);
+    if (n <= 0) die("cannot locate the executable");
+    self[n] = 0;
+    std::string root = self;
+    for (int up = 0; up < 3; ++up) {
+        size_t k = root.find_last_of('/');
+        if (k == std::string::npos) die("cannot locate the Python package next to the executable");
+        root.resize(k);
+    }
+    const char* old = std::getenv("PYTHONPATH");
+    std::string pp = root + (old && *old ? std::string(":") + old : std::string());
+    setenv("PYTHONPATH", pp.c_str(), 1);
+    std::vector<char*> args;
+    const char* py = std::getenv("NRRT_PYTHON");
+    std::string python = py && *py ? py : "python3";
+    args.push_back(const_cast<char*>(python.c_str()));
+    args.push_back(const_cast<char*>("-m"));
+    args.push_back(const_cast<char*>("nr_ray_tracer_b200.create"));
+    for (int i = 2; i < argc; ++i) args.push_back(argv[i]);
+    args.push_back(nullptr);
+    execvp(args[0], args.data());
+    die(std::string("cannot run ") + python + ": " + std::strerror(errno));
+}
+
 int main(int argc, char** argv) {
     if (argc < 2 || std::strcmp(argv[1], "--help") == 0 || std::strcmp(argv[1], "-h") == 0) {
         usage();
         return argc < 2 ? 2 : 0;
     }
-    if (std::strcmp(argv[1], "render") != 0) die(std::string("unknown command '") + argv[1] + "' (only `render` runs on the GPU path)");
+    if (std::strcmp(argv[1], "create") == 0) return run_create(argc, argv);
+    if (std::strcmp(argv[1], "render") != 0) die(std::string("unknown command '") + argv[1] + "' (commands: render, create)");
     std::string scene_path, output = "out.png", mode = "fused", bvh = "reference";
     bool force = false, verbose = false;
     float gamma = 0.5f;  // constants.rs:1

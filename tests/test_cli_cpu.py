@@ -45,3 +45,15 @@ def test_output_file_is_not_overwritten_without_force(tmp_path):
 def test_render_without_a_gpu_fails_loudly(tmp_path):
     r = run("render", QUADS, "-o", str(tmp_path / "q.png"), "-W", "16", "-H", "9")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_create_subcommand_hands_over_to_the_generators(tmp_path):
+    """The binary keeps the reference's two subcommands: `create` runs the Python generators (create.py)."""
+    from nr_ray_tracer_b200 import create
+    out = tmp_path / "cube.json"
+    r = run("create", "cube", "-o", str(out), env={"NRRT_PYTHON": __import__("sys").executable})
+    assert r.returncode == 0, r.stderr
+    assert out.read_text() == create.dumps(create.cube(), "json") + "\n"
+    r = run("create", "quads", env={"NRRT_PYTHON": __import__("sys").executable})
+    assert r.returncode == 0 and r.stdout == create.dumps(create.quads(), "toml") + "\n"
+    assert run("create", "nonsense", env={"NRRT_PYTHON": __import__("sys").executable}).returncode != 0

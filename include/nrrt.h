@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NRRT_ABI_VERSION 3
+#define NRRT_ABI_VERSION 4
 
 /* ---- status codes ------------------------------------------------------ */
 enum {
@@ -181,6 +181,24 @@ typedef struct nrrt_box {
     double hi[3];
 } nrrt_box;
 
+/* 128-byte four-slot traversal node (one cache line, 8 x LDG.128): the binary tree above with every other level
+ * folded away.  A wide node stands for one binary node B; its slots hold B's grandchildren in depth-first order
+ * (or, where a child of B is a leaf, that child), so the leaves, their depth-first order and therefore every
+ * tie-break (object.rs:110-114) are those of the binary tree, while a ray makes half as many dependent fetches.
+ * What the reference tests on the way to a slot is kept exactly:
+ *   - a slot that is an inner node must pass its own box test (object.rs:102);
+ *   - a slot whose binary parent was folded away ("gated", meta bit 0) additionally needs that parent's box test
+ *     to pass.  The parent's box encloses the slot's box and the slab test is monotone under IEEE rounding, so a
+ *     slot box that certainly passes implies the gate passes; only inconclusive slots evaluate the gate in f64.
+ * Leaves are not box-tested by the reference (object.rs:95-97): their slot box only culls what certainly misses. */
+typedef struct nrrt_wnode {
+    float lo[3][4];    /* lo[axis][slot], nearest-rounded from the f64 boxes */
+    float hi[3][4];
+    uint32_t child[4]; /* ref per slot (wide-node index for NODE refs); NRRT_REF_NONE = unused slot */
+    uint32_t meta[4];  /* bit 0: gated slot */
+} nrrt_wnode;
+#define NRRT_WNODE_GATED 1u
+
 /* One wrapper of an instance chain, outermost first. */
 enum nrrt_xform_kind { NRRT_XF_TRANSLATE = 0, NRRT_XF_ROTATE = 1, NRRT_XF_SCALE = 2 };
 typedef struct nrrt_xform {
@@ -248,11 +266,20 @@ typedef struct nrrt_scene_desc {
     uint32_t n_images;
     const nrrt_image* images;
 
-    uint32_t max_stack; /* worst-case traversal stack entries (validated by the host) */
+    uint32_t max_stack; /* worst-case traversal stack entries over the four-slot nodes (validated by the host) */
 
     /* moving spheres (sphere.rs:110-111): speed vector per sphere, or NULL when no sphere moves (every shipped
      * scene); kept out of sphere_rec so static scenes keep the 32-byte record */
     const double* sphere_speed; /* [n][3] or NULL */
+
+    /* Four-slot traversal nodes: what the kernels walk (nodes / child_boxes above describe the same trees in binary
+     * form and stay on the host).  wide_boxes[8*i + 2*s] = exact box of slot s of wide node i (inner-node slots),
+     * wide_boxes[8*i + 2*s + 1] = exact box of its folded-away binary parent (gated slots). */
+    uint32_t n_wnodes;
+    const nrrt_wnode* wnodes;            /* [n_wnodes] */
+    const nrrt_box* wide_boxes;          /* [8*n_wnodes] */
+    uint32_t wide_root;                  /* `root` as a wide ref */
+    const uint32_t* instance_wide_inner; /* [n_instances]: instances[i].inner as a wide ref */
 } nrrt_scene_desc;
 
 #define NRRT_PLANE_TRIANGLE_BIT 0x80000000u
@@ -415,9 +442,9 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* camera, const nrrt_render_opts
 int nrrt_encode_rgb8(nrrt_ctx* ctx, const float* rgb, uint32_t width, uint32_t height, float gamma, uint32_t flags,
                      uint8_t* out_rgb8);
 
-/* sizeof() of the ABI structs as compiled (which = 0..16 in header order: object, material, texture,
+/* sizeof() of the ABI structs as compiled (which = 0..17: object, material, texture,
  * image, graph_desc, camera_config, camera, node, box, xform, instance, scene_desc, hit, trace_stats,
- * render_opts, render_stats, camera_file) so a binding can verify its mirror of this header. */
+ * render_opts, render_stats, camera_file, wnode) so a binding can verify its mirror of this header. */
 size_t nrrt_abi_sizeof(int which);
 
 #ifdef __cplusplus

@@ -5,7 +5,7 @@ struct sizes against the values the compiled library reports.
 """
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 BUILD_REFERENCE, BUILD_SAH = 0, 1
 
 # status codes
@@ -78,6 +78,13 @@ class Box(C.Structure):
     _fields_ = [("lo", f64 * 3), ("hi", f64 * 3)]
 
 
+class WNode(C.Structure):
+    _fields_ = [("lo", (f32 * 4) * 3), ("hi", (f32 * 4) * 3), ("child", u32 * 4), ("meta", u32 * 4)]
+
+
+WNODE_GATED = 1
+
+
 class Xform(C.Structure):
     _fields_ = [("kind", u32), ("_pad", u32), ("to_obj", f64 * 12), ("to_world", f64 * 12)]
 
@@ -102,6 +109,8 @@ class SceneDesc(C.Structure):
         ("n_images", u32), ("images", C.POINTER(Image)),
         ("max_stack", u32),
         ("sphere_speed", C.POINTER(f64)),
+        ("n_wnodes", u32), ("wnodes", C.POINTER(WNode)), ("wide_boxes", C.POINTER(Box)),
+        ("wide_root", u32), ("instance_wide_inner", C.POINTER(u32)),
     ]
 
 

@@ -76,7 +76,7 @@ def lib() -> C.CDLL:
 
 
 ABI_STRUCTS = [A.Object, A.Material, A.Texture, A.Image, A.GraphDesc, A.CameraConfig, A.Camera, A.Node, A.Box,
-               A.Xform, A.Instance, A.SceneDesc, A.Hit, A.TraceStats, A.RenderOpts, A.RenderStats, A.CameraFile]
+               A.Xform, A.Instance, A.SceneDesc, A.Hit, A.TraceStats, A.RenderOpts, A.RenderStats, A.CameraFile, A.WNode]
 
 
 def camera_build(cfg: A.CameraConfig) -> A.Camera:
@@ -167,6 +167,28 @@ class HostScene:
             return np.zeros((0, 2, 2, 3))
         a = np.ctypeslib.as_array(C.cast(self.desc.child_boxes, C.POINTER(C.c_double)), shape=(n, 2, 2, 3))
         return a.copy()
+
+    def wnodes(self) -> np.ndarray:
+        """The four-slot traversal nodes the kernels walk (nrrt_wnode)."""
+        n = self.desc.n_wnodes
+        dt = np.dtype([("lo", "<f4", (3, 4)), ("hi", "<f4", (3, 4)), ("child", "<u4", (4,)), ("meta", "<u4", (4,))])
+        if n == 0:
+            return np.zeros(0, dtype=dt)
+        return np.ctypeslib.as_array(C.cast(self.desc.wnodes, C.POINTER(C.c_uint8)), shape=(n * 128,)).view(dt).copy()
+
+    def wide_boxes(self) -> np.ndarray:
+        """(n_wnodes, 4 slots, own / gate, lo / hi, 3) exact f64 boxes."""
+        n = self.desc.n_wnodes
+        if n == 0:
+            return np.zeros((0, 4, 2, 2, 3))
+        a = np.ctypeslib.as_array(C.cast(self.desc.wide_boxes, C.POINTER(C.c_double)), shape=(n, 4, 2, 2, 3))
+        return a.copy()
+
+    def instance_wide_inner(self) -> np.ndarray:
+        n = self.desc.n_instances
+        if n == 0:
+            return np.zeros(0, dtype=np.uint32)
+        return np.ctypeslib.as_array(self.desc.instance_wide_inner, shape=(n,)).copy()
 
 
 class Context:

@@ -492,6 +492,99 @@ struct Flattener {
         return Emitted{NRRT_REF(NRRT_REF_INSTANCE, idx), info[oi].box, depth + 1, levels + 1};
     }
 
+    // ---- four-slot nodes (nrrt_wnode): every other level of the binary trees folded away.  Runs after the binary
+    // flattening; binary node b becomes wide node wide_of[b] whose slots are b's grandchildren (or b's child where
+    // that child is a leaf), in depth-first order.  Only nodes reachable as a space root or as a slot are emitted.
+    std::vector<nrrt_wnode> wnodes;
+    std::vector<nrrt_box> wide_boxes;
+    std::vector<uint32_t> wide_of;              // binary node -> wide node, 0xFFFFFFFF = not (yet) emitted
+    std::vector<uint32_t> instance_wide_inner;  // per instance
+    std::vector<uint32_t> wide_need;            // per wide node: traversal stack entries needed below it
+
+    uint32_t wide_ref(uint32_t ref) {  // binary ref -> wide ref (emits the subtree on first use)
+        if (ref == NRRT_REF_NONE || NRRT_REF_TYPE(ref) != NRRT_REF_NODE) return ref;
+        return NRRT_REF(NRRT_REF_NODE, emit_wide(NRRT_REF_INDEX(ref)));
+    }
+    uint32_t emit_wide(uint32_t b) {
+        if (wide_of[b] != 0xFFFFFFFFu) return wide_of[b];
+        const uint32_t w = (uint32_t)wnodes.size();
+        if (w >= NRRT_REF_INDEX_MASK) fail("too many BVH nodes");
+        wide_of[b] = w;
+        wnodes.emplace_back();
+        wide_need.push_back(0);
+        for (int k = 0; k < 8; ++k) wide_boxes.push_back(to_box(Aabb::empty()));
+        struct Slot {
+            uint32_t ref;       // binary ref
+            nrrt_box box;       // the slot's own box
+            nrrt_box gate;      // box of the folded-away parent
+            bool gated;
+        };
+        Slot slots[4];
+        int n = 0;
+        const nrrt_node nb = nodes[b];
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t r = nb.child[c];
+            if (r == NRRT_REF_NONE) continue;
+            if (NRRT_REF_TYPE(r) == NRRT_REF_NODE) {
+                const uint32_t b2 = NRRT_REF_INDEX(r);
+                const nrrt_node n2 = nodes[b2];
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    if (n2.child[c2] == NRRT_REF_NONE) continue;
+                    slots[n++] = Slot{n2.child[c2], child_boxes[2 * (size_t)b2 + c2], child_boxes[2 * (size_t)b + c], true};
+                }
+            } else {
+                slots[n++] = Slot{r, child_boxes[2 * (size_t)b + c], to_box(Aabb::empty()), false};
+            }
+        }
+        nrrt_wnode wn;
+        std::memset(&wn, 0, sizeof wn);
+        const float inf = std::numeric_limits<float>::infinity();
+        uint32_t need = 0;
+        for (int s = 0; s < 4; ++s) {
+            if (s >= n) {  // unused slot: an empty box and no child
+                for (int a = 0; a < 3; ++a) wn.lo[a][s] = inf, wn.hi[a][s] = -inf;
+                wn.child[s] = NRRT_REF_NONE;
+                continue;
+            }
+            for (int a = 0; a < 3; ++a) wn.lo[a][s] = (float)slots[s].box.lo[a], wn.hi[a][s] = (float)slots[s].box.hi[a];
+            wn.meta[s] = slots[s].gated ? NRRT_WNODE_GATED : 0u;
+            wide_boxes[8 * (size_t)w + 2 * s] = slots[s].box;
+            wide_boxes[8 * (size_t)w + 2 * s + 1] = slots[s].gate;
+            const uint32_t wr = wide_ref(slots[s].ref);  // recursion: depth-first, so slot order = leaf order
+            wn.child[s] = wr;
+            uint32_t below = 0;
+            if (NRRT_REF_TYPE(wr) == NRRT_REF_NODE) below = wide_need[NRRT_REF_INDEX(wr)];
+            else if (NRRT_REF_TYPE(wr) == NRRT_REF_INSTANCE) below = instance_need(NRRT_REF_INDEX(wr));
+            need = std::max(need, below);
+        }
+        // all but the slot being descended into wait on the stack
+        wide_need[w] = need + (n > 0 ? (uint32_t)n - 1 : 0);
+        wnodes[w] = wn;
+        return w;
+    }
+    // entering an instance leaves a level marker on the stack, then traverses the nested space
+    uint32_t instance_need(uint32_t i) {
+        const uint32_t wr = wide_ref(instances[i].inner);
+        instance_wide_inner[i] = wr;
+        uint32_t below = 0;
+        if (wr != NRRT_REF_NONE && NRRT_REF_TYPE(wr) == NRRT_REF_NODE) below = wide_need[NRRT_REF_INDEX(wr)];
+        else if (wr != NRRT_REF_NONE && NRRT_REF_TYPE(wr) == NRRT_REF_INSTANCE) below = instance_need(NRRT_REF_INDEX(wr));
+        return below + 1;
+    }
+    // returns the wide root ref and the worst-case stack need of the whole scene
+    uint32_t build_wide(uint32_t root_ref, uint32_t& max_stack) {
+        wide_of.assign(nodes.size(), 0xFFFFFFFFu);
+        instance_wide_inner.assign(instances.size(), NRRT_REF_NONE);
+        const uint32_t wr = wide_ref(root_ref);
+        uint32_t need = 0;
+        if (wr != NRRT_REF_NONE && NRRT_REF_TYPE(wr) == NRRT_REF_NODE) need = wide_need[NRRT_REF_INDEX(wr)];
+        else if (wr != NRRT_REF_NONE && NRRT_REF_TYPE(wr) == NRRT_REF_INSTANCE) need = instance_need(NRRT_REF_INDEX(wr));
+        for (uint32_t i = 0; i < instances.size(); ++i)  // instances the root never reaches cannot exist, but be safe
+            if (instance_wide_inner[i] == NRRT_REF_NONE && instances[i].inner != NRRT_REF_NONE) instance_need(i);
+        max_stack = need + 2;
+        return wr;
+    }
+
     nrrt_xform make_xform(const nrrt_object& o) const {
         nrrt_xform x;
         std::memset(&x, 0, sizeof x);
@@ -617,8 +710,14 @@ nrrt_host_scene* nrrt_host_build_ex(const nrrt_graph_desc* g, uint32_t flags) {
         d.textures = hs->textures.data();
         d.n_images = (uint32_t)hs->images.size();
         d.images = hs->images.data();
-        d.max_stack = root.depth + 2;
         d.sphere_speed = f.any_motion ? f.sphere_speed.data() : nullptr;
+        uint32_t wide_stack = 0;
+        d.wide_root = f.build_wide(root.ref, wide_stack);
+        d.max_stack = wide_stack;
+        d.n_wnodes = (uint32_t)f.wnodes.size();
+        d.wnodes = f.wnodes.data();
+        d.wide_boxes = f.wide_boxes.data();
+        d.instance_wide_inner = f.instance_wide_inner.data();
         return hs.release();
     } catch (const HostError& e) {
         g_error = e.msg;

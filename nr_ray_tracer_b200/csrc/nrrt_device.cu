@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <thread>
 #include <chrono>
@@ -898,15 +899,112 @@ int nrrt_set_trace_time(nrrt_ctx* ctx, double time) {
 
 static uint32_t pick_features(uint32_t need);
 
+// The flat scene is plain caller memory: check every reference and index the kernels will follow, and recompute the
+// traversal stack need instead of trusting max_stack, so a stale or corrupted description is refused here rather than
+// overrunning a thread's shared-memory stack or reading out of bounds on the device.  Returns "" when sound.
+static std::string validate_scene_desc(const nrrt_scene_desc* sc) {
+    auto need_ptr = [](const void* p, uint64_t n) { return n == 0 || p != nullptr; };
+    if (!need_ptr(sc->wnodes, sc->n_wnodes) || !need_ptr(sc->wide_boxes, sc->n_wnodes)) return "wide node arrays missing";
+    if (!need_ptr(sc->sphere_rec, sc->n_spheres) || !need_ptr(sc->sphere_material, sc->n_spheres) ||
+        !need_ptr(sc->sphere_order, sc->n_spheres) || !need_ptr(sc->sphere_object, sc->n_spheres))
+        return "sphere arrays missing";
+    if (!need_ptr(sc->plane_rec, sc->n_planes) || !need_ptr(sc->plane_material, sc->n_planes) ||
+        !need_ptr(sc->plane_order, sc->n_planes) || !need_ptr(sc->plane_object, sc->n_planes))
+        return "plane arrays missing";
+    if (!need_ptr(sc->instances, sc->n_instances) || !need_ptr(sc->instance_order, sc->n_instances) ||
+        !need_ptr(sc->instance_wide_inner, sc->n_instances) || !need_ptr(sc->xforms, sc->n_xforms))
+        return "instance arrays missing";
+    if (!need_ptr(sc->materials, sc->n_materials) || !need_ptr(sc->textures, sc->n_textures) ||
+        !need_ptr(sc->images, sc->n_images))
+        return "shading tables missing";
+    auto ref_ok = [&](uint32_t r) {
+        if (r == NRRT_REF_NONE) return true;
+        const uint32_t ix = NRRT_REF_INDEX(r);
+        switch (NRRT_REF_TYPE(r)) {
+            case NRRT_REF_NODE: return ix < sc->n_wnodes;
+            case NRRT_REF_SPHERE: return ix < sc->n_spheres;
+            case NRRT_REF_PLANE: return ix < sc->n_planes;
+            case NRRT_REF_INSTANCE: return ix < sc->n_instances;
+            default: return false;
+        }
+    };
+    if (!ref_ok(sc->wide_root)) return "root reference out of range";
+    for (uint32_t i = 0; i < sc->n_wnodes; ++i)
+        for (int s = 0; s < 4; ++s) {
+            const uint32_t r = sc->wnodes[i].child[s];
+            if (!ref_ok(r)) return "node child reference out of range";
+            if (r != NRRT_REF_NONE && NRRT_REF_TYPE(r) == NRRT_REF_NODE && NRRT_REF_INDEX(r) <= i)
+                return "node children must follow their parent (depth-first order)";  // also rules out cycles
+        }
+    for (uint32_t i = 0; i < sc->n_instances; ++i) {
+        const nrrt_instance& in = sc->instances[i];
+        if (!ref_ok(sc->instance_wide_inner[i])) return "instance inner reference out of range";
+        if ((uint64_t)in.first_xform + in.n_xforms > sc->n_xforms) return "instance transform range out of bounds";
+    }
+    for (uint32_t i = 0; i < sc->n_xforms; ++i)
+        if (sc->xforms[i].kind > NRRT_XF_SCALE) return "unknown transform kind";
+    for (uint32_t i = 0; i < sc->n_spheres; ++i)
+        if (sc->sphere_material[i] >= sc->n_materials) return "sphere material out of range";
+    for (uint32_t i = 0; i < sc->n_planes; ++i)
+        if ((sc->plane_material[i] & ~NRRT_PLANE_TRIANGLE_BIT) >= sc->n_materials) return "plane material out of range";
+    for (uint32_t i = 0; i < sc->n_materials; ++i) {
+        const nrrt_material& m = sc->materials[i];
+        if (m.kind > NRRT_MAT_DIFFUSE_LIGHT) return "unknown material kind";
+        if (m.kind != NRRT_MAT_DIELECTRIC && m.texture >= sc->n_textures) return "material texture out of range";
+    }
+    for (uint32_t i = 0; i < sc->n_textures; ++i) {
+        const nrrt_texture& t = sc->textures[i];
+        if (t.kind > NRRT_TEX_MARBLE) return "unknown texture kind";
+        if (t.kind == NRRT_TEX_CHECKER && (t.a >= i || t.b >= i)) return "checker sub-textures must precede the checker";
+        if (t.kind == NRRT_TEX_IMAGE && t.a >= sc->n_images) return "image index out of range";
+    }
+    // worst-case stack need: node -> node edges only go to larger indices, so one reverse sweep settles a space;
+    // instances reach into other spaces (possibly emitted earlier), so sweep until nothing changes — one sweep per
+    // nesting level; still changing after NRRT_MAX_INSTANCE_DEPTH + 1 sweeps means too deep a nesting or a cycle
+    std::vector<uint32_t> need(sc->n_wnodes, 0), inst_need(sc->n_instances, 1);
+    auto below = [&](uint32_t r) -> uint32_t {
+        if (r == NRRT_REF_NONE) return 0;
+        if (NRRT_REF_TYPE(r) == NRRT_REF_NODE) return need[NRRT_REF_INDEX(r)];
+        if (NRRT_REF_TYPE(r) == NRRT_REF_INSTANCE) return inst_need[NRRT_REF_INDEX(r)];
+        return 0;
+    };
+    for (int sweep = 0;; ++sweep) {
+        bool changed = false;
+        for (uint32_t i = sc->n_wnodes; i-- > 0;) {
+            uint32_t deepest = 0, n = 0;
+            for (int s = 0; s < 4; ++s) {
+                const uint32_t r = sc->wnodes[i].child[s];
+                if (r == NRRT_REF_NONE) continue;
+                ++n;
+                deepest = std::max(deepest, below(r));
+            }
+            const uint32_t v = deepest + (n ? n - 1 : 0);
+            if (v != need[i]) need[i] = v, changed = true;
+        }
+        for (uint32_t i = 0; i < sc->n_instances; ++i) {
+            const uint32_t v = below(sc->instance_wide_inner[i]) + 1;  // the level marker
+            if (v != inst_need[i]) inst_need[i] = v, changed = true;
+        }
+        if (!changed) break;
+        if (sweep > NRRT_MAX_INSTANCE_DEPTH + 1) return "instances nest deeper than NRRT_MAX_INSTANCE_DEPTH (or form a cycle)";
+    }
+    const uint32_t total = below(sc->wide_root);
+    if (total + 2 > NRRT_STACK_CAP) return "scene needs a deeper traversal stack than NRRT_STACK_CAP";
+    return "";
+}
+
 int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
     if (!ctx || !sc) return NRRT_ERR_INVALID;
     if (sc->abi_version != NRRT_ABI_VERSION) {
         ctx->err = "scene desc ABI version mismatch";
         return NRRT_ERR_INVALID;
     }
-    if (sc->max_stack > NRRT_STACK_CAP) {
-        ctx->err = "scene needs a deeper traversal stack than NRRT_STACK_CAP";
-        return NRRT_ERR_LIMIT;
+    {
+        std::string why = validate_scene_desc(sc);
+        if (!why.empty()) {
+            ctx->err = "nrrt_scene_upload: " + why;
+            return why.find("stack") != std::string::npos ? NRRT_ERR_LIMIT : NRRT_ERR_INVALID;
+        }
     }
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -918,14 +1016,14 @@ int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
         free_scene(ctx);                                                \
         return rc;                                                      \
     }
-    const float4* nodes4 = nullptr;
-    if ((rc = upload(ctx, (const float4*)sc->nodes, (size_t)sc->n_nodes * 4, &nodes4)) != NRRT_OK) {
+    const float4* wnodes4 = nullptr;
+    if ((rc = upload(ctx, (const float4*)sc->wnodes, (size_t)sc->n_wnodes * 8, &wnodes4)) != NRRT_OK) {
         free_scene(ctx);
         return rc;
     }
-    D.nodes = nodes4;
-    UP(child_boxes, sc->child_boxes, (size_t)sc->n_nodes * 2);
-    D.root = sc->root;
+    D.wnodes = wnodes4;
+    UP(wide_boxes, sc->wide_boxes, (size_t)sc->n_wnodes * 8);
+    D.root = sc->wide_root;
     D.root_box = sc->root_box;
     UP(sphere_rec, sc->sphere_rec, (size_t)sc->n_spheres * 4);
     if (sc->n_spheres && sc->sphere_speed) {
@@ -940,7 +1038,9 @@ int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
     UP(plane_material, sc->plane_material, sc->n_planes);
     UP(plane_order, sc->plane_order, sc->n_planes);
     UP(plane_object, sc->plane_object, sc->n_planes);
-    UP(instances, sc->instances, sc->n_instances);
+    std::vector<nrrt_instance> inst(sc->instances, sc->instances + sc->n_instances);
+    for (uint32_t i = 0; i < sc->n_instances; ++i) inst[i].inner = sc->instance_wide_inner[i];  // the kernels walk wide nodes
+    UP(instances, inst.data(), inst.size());
     UP(instance_order, sc->instance_order, sc->n_instances);
     UP(xforms, sc->xforms, sc->n_xforms);
     UP(materials, sc->materials, sc->n_materials);
@@ -1521,6 +1621,7 @@ size_t nrrt_abi_sizeof(int which) {
         case 14: return sizeof(nrrt_render_opts);
         case 15: return sizeof(nrrt_render_stats);
         case 16: return sizeof(nrrt_camera_file);
+        case 17: return sizeof(nrrt_wnode);
         default: return 0;
     }
 }

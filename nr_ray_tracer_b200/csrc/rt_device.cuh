@@ -40,9 +40,9 @@
 
 // --------------------------------------------------------------------------- device scene
 struct DevScene {
-    const float4* nodes;  // 4 x float4 per node
-    const nrrt_box* child_boxes;
-    uint32_t root;
+    const float4* wnodes;  // four-slot nodes (nrrt_wnode), 8 x float4 each
+    const nrrt_box* wide_boxes;  // [8 * n]: own box / gate box per slot
+    uint32_t root;         // wide ref
     nrrt_box root_box;
     const double* sphere_rec;  // [n][4]: center xyz, radius
     const double* sphere_speed;  // [n][3] or nullptr when no sphere moves
@@ -351,6 +351,83 @@ __device__ __forceinline__ bool root_box_test(const nrrt_box* b, const Ray32& r3
     return box_hit_exact(b, o, d, tmin, tmax);
 }
 
+// ---- one visit of a four-slot node (nrrt_wnode, include/nrrt.h)
+__device__ __forceinline__ uint32_t pick4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t i) {
+    const uint32_t lo = (i & 1u) ? b : a, hi = (i & 1u) ? d : c;
+    return (i & 2u) ? hi : lo;
+}
+__device__ __forceinline__ void cswap(uint32_t& a, uint32_t& b) {
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    a = lo, b = hi;
+}
+// Tests the four slot boxes of wide node `ni` with the f32 filter (inconclusive slots: the reference's exact f64 tests,
+// gate first, then the slot's own box if it is an inner node), drops what starts certainly behind the best hit
+// (tcull; not with VISIT_ALL), and returns the visited slots' refs sorted near to far in out[0..n).
+// load_exact_ray(o, d) fetches the f64 ray of the current space; it is only called on the rare inconclusive path.
+template <bool VISIT_ALL, bool COUNT, class LoadRay>
+__device__ __forceinline__ uint32_t wide_visit(const DevScene& S, const Ray32& r32, float tmin32, float tmax32,
+                                               float tcull, uint32_t ni, double tmin, double tmax, LoadRay&& load_exact_ray,
+                                               TraceCounters* cnt, uint32_t (&out)[4]) {
+    const float4* np = S.wnodes + 8 * (size_t)ni;
+    const float4 LX = __ldg(np), LY = __ldg(np + 1), LZ = __ldg(np + 2), HX = __ldg(np + 3), HY = __ldg(np + 4),
+                 HZ = __ldg(np + 5);
+    const uint4 CH = __ldg(reinterpret_cast<const uint4*>(np + 6));
+    const float lx[4] = {LX.x, LX.y, LX.z, LX.w}, ly[4] = {LY.x, LY.y, LY.z, LY.w}, lz[4] = {LZ.x, LZ.y, LZ.z, LZ.w};
+    const float hx[4] = {HX.x, HX.y, HX.z, HX.w}, hy[4] = {HY.x, HY.y, HY.z, HY.w}, hz[4] = {HZ.x, HZ.y, HZ.z, HZ.w};
+    const uint32_t ch[4] = {CH.x, CH.y, CH.z, CH.w};
+    if (COUNT) cnt->nodes++;
+    float e[4], m[4];
+    bool v[4], amb[4], any_amb = false;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        float g;
+        box_filter(r32, lx[s], ly[s], lz[s], hx[s], hy[s], hz[s], tmin32, tmax32, e[s], g, m[s]);
+        // leaves are not box-tested by the reference (object.rs:95-97): visit unless certainly missed; inner slots
+        // and gated slots must pass the reference's tests: certain from the filter, else exact
+        v[s] = (ch[s] != NRRT_REF_NONE) && !(g < -m[s]);
+        amb[s] = v[s] && !(g >= m[s]);
+        any_amb = any_amb || amb[s];
+    }
+    if (any_amb) {  // rare
+        const uint4 ME = __ldg(reinterpret_cast<const uint4*>(np + 7));
+        const uint32_t me[4] = {ME.x, ME.y, ME.z, ME.w};
+        d3 o, d;
+        load_exact_ray(o, d);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (!amb[s]) continue;
+            bool ok = true;
+            if (me[s] & NRRT_WNODE_GATED) {
+                if (COUNT) cnt->exact++;
+                ok = box_hit_exact(S.wide_boxes + 8 * (size_t)ni + 2 * s + 1, o, d, tmin, tmax);
+            }
+            if (ok && NRRT_REF_TYPE(ch[s]) == NRRT_REF_NODE) {
+                if (COUNT) cnt->exact++;
+                ok = box_hit_exact(S.wide_boxes + 8 * (size_t)ni + 2 * s, o, d, tmin, tmax);
+            }
+            v[s] = ok;
+        }
+    }
+    uint32_t k[4], n = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        // prune slots that start certainly behind the best hit (ties are kept: margin > 0)
+        if (!VISIT_ALL) v[s] = v[s] && !(e[s] - m[s] > tcull);
+        n += v[s] ? 1u : 0u;
+        // sort key: entry distance (non-negative for tmin >= 0, so its bit pattern orders like the value) with the
+        // slot number in the two low bits; the order only affects how soon the best hit shrinks the search
+        k[s] = v[s] ? (VISIT_ALL ? (uint32_t)s : ((__float_as_uint(e[s]) & ~3u) | (uint32_t)s)) : 0xFFFFFFFFu;
+    }
+    cswap(k[0], k[1]);
+    cswap(k[2], k[3]);
+    cswap(k[0], k[2]);
+    cswap(k[1], k[3]);
+    cswap(k[1], k[2]);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) out[s] = pick4(ch[0], ch[1], ch[2], ch[3], k[s] & 3u);
+    return n;
+}
+
 // Per-query context handed to begin()/round() on every call instead of being stored in the traversal state, so
 // base pointers are re-read from the kernel's constant bank rather than pinned in registers.
 //   get(): the world-space ray (needed again when an instance is left)
@@ -508,46 +585,16 @@ struct Traversal {
                 if (kSpeculate) continue;
                 break;
             }
-            uint32_t ni = NRRT_REF_INDEX(cur);
-            const float4* np = S.nodes + 4 * (size_t)ni;
-            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-            // layout: lo[0].xyz lo[1].xyz | hi[0].xyz hi[1].xyz | child[0] child[1] pad pad
-            uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
-            if (COUNT) cnt->nodes++;
-            float e0, g0, m0, e1, g1, m1;
-            box_filter(r32, n0.x, n0.y, n0.z, n1.z, n1.w, n2.x, tmin32, tmax32, e0, g0, m0);
-            box_filter(r32, n0.w, n1.x, n1.y, n2.y, n2.z, n2.w, tmin32, tmax32, e1, g1, m1);
-            // leaves are not box-tested by the reference (object.rs:95-97): visit unless certainly missed;
-            // inner children must pass the reference's test: certain from the filter, else exact
-            bool v0 = (c0 != NRRT_REF_NONE) && !(g0 < -m0);
-            bool v1 = (c1 != NRRT_REF_NONE) && !(g1 < -m1);
-            bool amb0 = v0 && NRRT_REF_TYPE(c0) == NRRT_REF_NODE && !(g0 >= m0);
-            bool amb1 = v1 && NRRT_REF_TYPE(c1) == NRRT_REF_NODE && !(g1 >= m1);
-            if (amb0 || amb1) {  // rare
-                d3 o, d;
-                load_ray(ctx, o, d);
-                if (amb0) {
-                    if (COUNT) cnt->exact++;
-                    v0 = box_hit_exact(S.child_boxes + 2 * (size_t)ni, o, d, tmin, tmax);
-                }
-                if (amb1) {
-                    if (COUNT) cnt->exact++;
-                    v1 = box_hit_exact(S.child_boxes + 2 * (size_t)ni + 1, o, d, tmin, tmax);
-                }
-            }
-            if (!VISIT_ALL) {
-                // prune children that start certainly behind the best hit (ties are kept: margin > 0)
-                v0 = v0 && !(e0 - m0 > tcull);
-                v1 = v1 && !(e1 - m1 > tcull);
-            }
-            if (v0 && v1) {
-                bool swap = !VISIT_ALL && (e1 < e0);
-                stack[sp * sstride] = swap ? c0 : c1;
-                ++sp;
-                cur = swap ? c1 : c0;
-            } else if (v0 || v1) {
-                cur = v0 ? c0 : c1;
-            } else {
+            uint32_t nxt[4];
+            const uint32_t n = wide_visit<VISIT_ALL, COUNT>(
+                S, r32, tmin32, tmax32, tcull, NRRT_REF_INDEX(cur), tmin, tmax,
+                [&](d3& oo, d3& dd) { load_ray(ctx, oo, dd); }, cnt, nxt);
+            // continue with the nearest slot, the others wait on the stack (farthest at the bottom)
+            if (n > 3) stack[sp * sstride] = nxt[3], ++sp;
+            if (n > 2) stack[sp * sstride] = nxt[2], ++sp;
+            if (n > 1) stack[sp * sstride] = nxt[1], ++sp;
+            cur = nxt[0];
+            if (n == 0) {
                 cur = NRRT_REF_NONE;
                 if (sp) {
                     --sp;

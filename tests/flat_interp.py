@@ -47,6 +47,11 @@ class FlatScene:
         self.inst = [d.instances[i] for i in range(d.n_instances)]
         self.inst_order = _arr(d.instance_order, d.n_instances, np.uint32)
         self.xf = [d.xforms[i] for i in range(d.n_xforms)]
+        # the four-slot nodes the kernels walk
+        self.wnodes = host_scene.wnodes()
+        self.wide_boxes = host_scene.wide_boxes()  # (n, 4 slots, own/gate, lo/hi, 3)
+        self.wide_root = d.wide_root
+        self.inst_wide_inner = host_scene.instance_wide_inner()
 
 
 def _dot(a, b):
@@ -109,8 +114,10 @@ def _mat4(m, v, point):
     return r
 
 
-def trace(fs: FlatScene, o, d, tmin=0.001, tmax=INF, tie_by_order=False):
+def trace(fs: FlatScene, o, d, tmin=0.001, tmax=INF, tie_by_order=False, wide=False):
     """Returns (t, object index, leaf order in the current space) of the reference's winner, or None.
+    wide=True walks the four-slot nodes (nrrt_wnode) with the exact tests the reference makes on the way to each
+    slot: the folded-away parent's box for gated slots, the slot's own box for inner nodes, nothing for leaves.
     tie_by_order=False: equal-t ties go to the later child of the flat tree (the reference rule on the reference
     tree).  tie_by_order=True: ties go to the leaf with the larger reference DFS order — what the kernels do, and
     the only rule that is right on an NRRT_BUILD_SAH tree, whose child order is not the reference's."""
@@ -119,6 +126,27 @@ def trace(fs: FlatScene, o, d, tmin=0.001, tmax=INF, tie_by_order=False):
         ty, ix = ref >> A.REF_TYPE_SHIFT, ref & A.REF_INDEX_MASK
         if ref == A.REF_NONE:
             return None
+        if ty == A.REF_NODE and wide:
+            wn = fs.wnodes[ix]
+            res = None
+            for sl in range(4):
+                cref = int(wn["child"][sl])
+                if cref == A.REF_NONE:
+                    continue
+                if int(wn["meta"][sl]) & A.WNODE_GATED:
+                    if not box_hit(fs.wide_boxes[ix, sl, 1, 0], fs.wide_boxes[ix, sl, 1, 1], o, d, tmin, tmax):
+                        continue
+                if (cref >> A.REF_TYPE_SHIFT) == A.REF_NODE:
+                    if not box_hit(fs.wide_boxes[ix, sl, 0, 0], fs.wide_boxes[ix, sl, 0, 1], o, d, tmin, tmax):
+                        continue
+                h = hit_ref(cref, o, d)
+                if h is None:
+                    continue
+                if res is None or h[0] < res[0]:
+                    res = h
+                elif h[0] == res[0] and (h[2] > res[2] if tie_by_order else True):  # ties -> later leaf
+                    res = h
+            return res
         if ty == A.REF_NODE:
             nd = fs.nodes[ix]
             res = None
@@ -181,7 +209,7 @@ def trace(fs: FlatScene, o, d, tmin=0.001, tmax=INF, tie_by_order=False):
                     oo, dd = _mat3(m, oo), _mat3(m, dd)
                 else:
                     oo, dd = _mat4(m, oo, True), _mat4(m, dd, False)
-            inner = ins.inner
+            inner = int(fs.inst_wide_inner[ix]) if wide else ins.inner
             if inner == A.REF_NONE:
                 return None
             if (inner >> A.REF_TYPE_SHIFT) == A.REF_NODE:
@@ -191,7 +219,7 @@ def trace(fs: FlatScene, o, d, tmin=0.001, tmax=INF, tie_by_order=False):
             return None if h is None else (h[0], h[1], int(fs.inst_order[ix]))
         return None
 
-    root = fs.root
+    root = fs.wide_root if wide else fs.root
     if root != A.REF_NONE and (root >> A.REF_TYPE_SHIFT) == A.REF_NODE:
         if not box_hit(fs.root_box[0], fs.root_box[1], o, d, tmin, tmax):
             return None

@@ -120,6 +120,62 @@ def test_flat_layout_traversed_with_reference_semantics_matches_oracle(name):
             assert h is not None and h[1] == ref["object"][i] and h[0] == ref["t"][i], (i, r, h, ref[i])
 
 
+@pytest.mark.parametrize("bvh", ["reference", "sah"])
+@pytest.mark.parametrize("name", ["spheres.toml", "cornell-box-scene.json", "scale.json", "cube-scene.json",
+                                  "simple-lights.toml", "utah-teapot-scene.json", "cornell-teapot-scene.json"])
+def test_four_slot_nodes_fold_the_binary_tree_and_give_the_oracle_hits(name, bvh):
+    """nrrt_wnode (what the kernels walk): every other level of the binary tree folded away.  Structure: each leaf in
+    exactly one slot, slots in depth-first leaf order, f32 slot boxes = the rounded f64 boxes, gates enclose their
+    slots, stack bound respected.  Semantics: walked with the reference's exact tests (gate box for gated slots, own
+    box for inner slots, none for leaves) it returns the oracle's hits, as the binary layout does."""
+    g = load(name)
+    hs = api.HostScene(g, bvh=bvh)
+    d = hs.desc
+    wn, wb = hs.wnodes(), hs.wide_boxes()
+    assert d.n_wnodes == len(wn) and d.max_stack <= 32
+    if d.n_nodes:
+        assert 0 < d.n_wnodes <= d.n_nodes
+    refs = wn["child"].reshape(-1)
+    used = refs != A.REF_NONE
+    types, idx = refs >> A.REF_TYPE_SHIFT, refs & A.REF_INDEX_MASK
+    # every leaf of the binary layout sits in exactly one slot (or is a space root / instance inner)
+    brefs = hs.nodes()["child"].reshape(-1)
+    bleaves = sorted(brefs[(brefs != A.REF_NONE) & ((brefs >> A.REF_TYPE_SHIFT) != A.REF_NODE)].tolist())
+    wleaves = sorted(refs[used & (types != A.REF_NODE)].tolist())
+    assert wleaves == bleaves
+    # every wide node is referenced exactly once (slot, scene root or a nested space's root)
+    roots = [int(d.wide_root)] + [int(r) for r in hs.instance_wide_inner()]
+    node_refs = sorted(idx[used & (types == A.REF_NODE)].tolist() +
+                       list({r & A.REF_INDEX_MASK for r in roots if r != A.REF_NONE and (r >> A.REF_TYPE_SHIFT) == A.REF_NODE}))
+    assert node_refs == list(range(d.n_wnodes))
+    lo32, hi32 = wn["lo"].transpose(0, 2, 1).reshape(-1, 3), wn["hi"].transpose(0, 2, 1).reshape(-1, 3)
+    own, gate = wb[:, :, 0].reshape(-1, 2, 3), wb[:, :, 1].reshape(-1, 2, 3)
+    assert np.array_equal(lo32[used], own[used][:, 0].astype(np.float32))
+    assert np.array_equal(hi32[used], own[used][:, 1].astype(np.float32))
+    assert np.isinf(lo32[~used]).all() and np.isinf(hi32[~used]).all()       # unused slots: empty boxes
+    gated = used & ((wn["meta"].reshape(-1) & A.WNODE_GATED) != 0)
+    assert gated.any() or d.n_nodes < 2
+    assert (gate[gated][:, 0] <= own[gated][:, 0]).all() and (gate[gated][:, 1] >= own[gated][:, 1]).all()
+    # slot order is depth-first leaf order: within one wide node of a primitive-only subtree, orders ascend
+    if bvh == "reference" and d.n_instances == 0 and d.n_spheres:
+        order = np.ctypeslib.as_array(d.sphere_order, shape=(d.n_spheres,))
+        for row in wn["child"]:
+            o = [int(order[r & A.REF_INDEX_MASK]) for r in row if r != A.REF_NONE and (r >> A.REF_TYPE_SHIFT) == A.REF_SPHERE]
+            assert o == sorted(o)
+    fs = flat_interp.FlatScene(hs)
+    sp = kat.special_rays(g)
+    rng = np.random.default_rng(1)
+    rays = np.concatenate([kat.random_rays(g, 200, seed=13), kat.aimed_rays(g, 300, seed=14),
+                           sp[rng.permutation(len(sp))[:250]]])
+    ref, _ = O.OracleScene(g).trace_rays(rays)
+    for i, r in enumerate(rays):
+        h = flat_interp.trace(fs, r[:3], r[3:], tie_by_order=(bvh == "sah"), wide=True)
+        if ref["object"][i] == 0xFFFFFFFF:
+            assert h is None, (i, r, h)
+        else:
+            assert h is not None and h[1] == ref["object"][i] and h[0] == ref["t"][i], (i, r, h, ref[i])
+
+
 @pytest.mark.parametrize("name", ALL_SCENES)
 def test_camera_build_matches_oracle_bit_for_bit(name):
     g = load(name, width=1920, height=1080)

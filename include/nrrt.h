@@ -392,8 +392,11 @@ int nrrt_trace_rays(nrrt_ctx* ctx, const double* rays, uint64_t n, double tmin, 
 enum nrrt_render_mode {
     NRRT_MODE_WAVEFRONT = 0, /* raygen / extend / shade+compact kernels over ray queues */
     NRRT_MODE_MEGAKERNEL = 1, /* one kernel, per-thread path loop, whole state in registers */
-    NRRT_MODE_FUSED = 2       /* persistent warps: traverse with warp-voted in-place shading, path state in
+    NRRT_MODE_FUSED = 2,      /* persistent warps: traverse with warp-voted in-place shading, path state in
                                  shared memory (no ray / hit-record round trips through HBM)   */
+    NRRT_MODE_POOL = 3        /* persistent warps, each scheduling a pool of path slots held in shared memory:
+                                 node / primitive / instance / shade stages run on whichever slots are ready,
+                                 so every stage runs with (nearly) all 32 lanes                  */
 };
 
 typedef struct nrrt_render_opts {

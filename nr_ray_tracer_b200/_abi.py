@@ -24,7 +24,7 @@ REF_TYPE_SHIFT = 29
 REF_INDEX_MASK = 0x1FFFFFFF
 
 TRACE_ORDERED, TRACE_VISIT_ALL, TRACE_DEVICE_BUFFERS, TRACE_COUNT = 0, 1, 2, 4
-MODE_WAVEFRONT, MODE_MEGAKERNEL, MODE_FUSED = 0, 1, 2
+MODE_WAVEFRONT, MODE_MEGAKERNEL, MODE_FUSED, MODE_POOL = 0, 1, 2, 3
 RENDER_OUT_HOST, RENDER_OUT_DEVICE, RENDER_COUNT = 0, 1, 2
 MAX_INSTANCE_DEPTH = 4
 

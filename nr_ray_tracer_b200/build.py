@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnrrt_b200.so")
 CLI = os.path.join(HERE, "bin", "nr-ray-tracer")
 SOURCES = ["nrrt_device.cu", "host_scene.cpp", "scene_loader.cpp"]
-HEADERS = ["rt_device.cuh", "host_math.hpp", "jpeg_baseline.hpp", os.path.join("..", "..", "include", "nrrt.h")]
+HEADERS = ["rt_device.cuh", "pool_kernel.cuh", "host_math.hpp", "jpeg_baseline.hpp", os.path.join("..", "..", "include", "nrrt.h")]
 
 
 def _nvcc() -> str:

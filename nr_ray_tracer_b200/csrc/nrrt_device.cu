@@ -361,7 +361,7 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
     s_px = s_py = s_end = 0;
     Sampler smp{P.key, 0u, 0u};
     uint32_t bounce = 0;
-    Traversal<false, false, F, SPEC> tr;
+    Traversal<false, false, F, SPEC, SPEC> tr;  // deep trees: four-slot nodes + speculation; small ones: binary nodes
 
     for (;;) {
         // ---- shading / regeneration round, voted by the warp
@@ -493,6 +493,8 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
         atomicAdd(&counters[1], s_cnt[1]);
     }
 }
+
+#include "pool_kernel.cuh"
 
 // ------------------------------------------------------------------ wavefront
 // SoA path state, one entry per slot (n = n_slots).
@@ -765,6 +767,8 @@ struct nrrt_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     unsigned persistent_blocks = 592;  // SMs x resident blocks of the extend kernel
+    unsigned sms = 148;                // multiprocessors
+    size_t smem_per_sm = 228 * 1024, smem_per_block = 227 * 1024;  // shared memory limits (opt-in)
     uint32_t features = NRRT_F_ALL;    // NRRT_F_* mask of the uploaded scene
     double trace_time = 0.0;           // Ray::time of nrrt_trace_rays queries
     bool speculate = false;            // fused kernel: speculative traversal (deep trees only)
@@ -855,8 +859,15 @@ int nrrt_create(int device, nrrt_ctx** out) {
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
     {
         int sms = 0;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) {
             ctx->persistent_blocks = (unsigned)sms * NRRT_EXTEND_MINBLOCKS;
+            ctx->sms = (unsigned)sms;
+        }
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device) == cudaSuccess && v > 0)
+            ctx->smem_per_sm = (size_t)v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess && v > 0)
+            ctx->smem_per_block = (size_t)v;
     }
     if ((e = cudaMalloc((void**)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess)
         return bail("cudaMalloc", e);
@@ -898,6 +909,55 @@ int nrrt_set_trace_time(nrrt_ctx* ctx, double time) {
 }
 
 static uint32_t pick_features(uint32_t need);
+#define NRRT_BINARY_MAX_NODES 64u  // scenes with fewer inner nodes are also uploaded in binary form (fused kernel)
+
+// Stack entries a traversal of the binary nodes can need, or a value above any cap when the arrays are unusable
+// (a reference out of range, children not after their parents).  Same sweep as for the four-slot nodes.
+static uint32_t binary_stack_need(const nrrt_scene_desc* sc) {
+    const uint32_t bad = 1u << 20;
+    if (!sc->nodes || !sc->child_boxes) return bad;
+    auto ok = [&](uint32_t r) {
+        if (r == NRRT_REF_NONE) return true;
+        const uint32_t ix = NRRT_REF_INDEX(r);
+        switch (NRRT_REF_TYPE(r)) {
+            case NRRT_REF_NODE: return ix < sc->n_nodes;
+            case NRRT_REF_SPHERE: return ix < sc->n_spheres;
+            case NRRT_REF_PLANE: return ix < sc->n_planes;
+            case NRRT_REF_INSTANCE: return ix < sc->n_instances;
+            default: return false;
+        }
+    };
+    if (!ok(sc->root)) return bad;
+    for (uint32_t i = 0; i < sc->n_instances; ++i)
+        if (!ok(sc->instances[i].inner)) return bad;
+    for (uint32_t i = 0; i < sc->n_nodes; ++i)
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t r = sc->nodes[i].child[c];
+            if (!ok(r)) return bad;
+            if (r != NRRT_REF_NONE && NRRT_REF_TYPE(r) == NRRT_REF_NODE && NRRT_REF_INDEX(r) <= i) return bad;
+        }
+    std::vector<uint32_t> need(sc->n_nodes, 0), inst_need(sc->n_instances, 1);
+    auto below = [&](uint32_t r) -> uint32_t {
+        if (r == NRRT_REF_NONE) return 0;
+        if (NRRT_REF_TYPE(r) == NRRT_REF_NODE) return need[NRRT_REF_INDEX(r)];
+        if (NRRT_REF_TYPE(r) == NRRT_REF_INSTANCE) return inst_need[NRRT_REF_INDEX(r)];
+        return 0;
+    };
+    for (int sweep = 0;; ++sweep) {
+        bool changed = false;
+        for (uint32_t i = sc->n_nodes; i-- > 0;) {
+            const uint32_t v = std::max(below(sc->nodes[i].child[0]), below(sc->nodes[i].child[1])) + 1;
+            if (v != need[i]) need[i] = v, changed = true;
+        }
+        for (uint32_t i = 0; i < sc->n_instances; ++i) {
+            const uint32_t v = below(sc->instances[i].inner) + 1;
+            if (v != inst_need[i]) inst_need[i] = v, changed = true;
+        }
+        if (!changed) break;
+        if (sweep > NRRT_MAX_INSTANCE_DEPTH + 1) return bad;
+    }
+    return below(sc->root);
+}
 
 // The flat scene is plain caller memory: check every reference and index the kernels will follow, and recompute the
 // traversal stack need instead of trusting max_stack, so a stale or corrupted description is refused here rather than
@@ -1025,6 +1085,22 @@ int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
     UP(wide_boxes, sc->wide_boxes, (size_t)sc->n_wnodes * 8);
     D.root = sc->wide_root;
     D.root_box = sc->root_box;
+    // small trees also go up in binary form (see DevScene::bnodes); validate_scene_desc checked them
+    const bool binary_ok = sc->nodes && sc->child_boxes && sc->n_nodes > 0 && sc->n_nodes < NRRT_BINARY_MAX_NODES &&
+                           binary_stack_need(sc) + 2 <= NRRT_STACK_CAP;
+    if (binary_ok) {
+        const float4* bn = nullptr;
+        if ((rc = upload(ctx, (const float4*)sc->nodes, (size_t)sc->n_nodes * 4, &bn)) != NRRT_OK) {
+            free_scene(ctx);
+            return rc;
+        }
+        D.bnodes = bn;
+        UP(bchild_boxes, sc->child_boxes, (size_t)sc->n_nodes * 2);
+        std::vector<uint32_t> binner(std::max<uint32_t>(sc->n_instances, 1), NRRT_REF_NONE);
+        for (uint32_t i = 0; i < sc->n_instances; ++i) binner[i] = sc->instances[i].inner;
+        UP(inst_binner, binner.data(), binner.size());
+        D.broot = sc->root;
+    }
     UP(sphere_rec, sc->sphere_rec, (size_t)sc->n_spheres * 4);
     if (sc->n_spheres && sc->sphere_speed) {
         UP(sphere_speed, sc->sphere_speed, (size_t)sc->n_spheres * 3);
@@ -1144,8 +1220,9 @@ int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
         ctx->features = pick_features(need);
         // speculative traversal pays once rays walk more than a handful of nodes (measured: Cornell's 17-node tree
         // loses 4 %, the 487-node sphere field gains 7 %, the 6319-node mesh 16 %)
-        ctx->speculate = sc->n_nodes >= 64;
+        ctx->speculate = sc->n_nodes >= NRRT_BINARY_MAX_NODES;
         if (const char* e = std::getenv("NRRT_SPECULATE")) ctx->speculate = std::atoi(e) != 0;  // developer override
+        if (!binary_ok) ctx->speculate = true;  // the plain instantiation walks the binary nodes
     }
     ctx->dev = D;
     ctx->max_stack = sc->max_stack;
@@ -1209,6 +1286,82 @@ static cudaError_t launch_fused(nrrt_ctx* ctx, unsigned blocks, const nrrt_camer
 #undef NRRT_FUSED_LAUNCH
     return e;
 }
+
+// ---- pooled kernel: launch geometry.  Shared memory bounds the slots in flight: pick the warps per block that
+// fits the most warps on an SM (each block also costs 1 KB of reserved shared memory).
+#ifndef NRRT_POOL_NS
+#define NRRT_POOL_NS 64  // path slots per warp
+#endif
+extern "C++" {
+struct PoolPlan {
+    unsigned warps_per_block = 0, blocks_per_sm = 0;
+    size_t smem = 0, cold_bytes_per_slot = 0;
+    uint32_t cap = 0;
+    uint64_t slots = 0;  // resident path slots on the whole GPU
+};
+template <uint32_t F>
+static PoolPlan pool_plan_f(const nrrt_ctx* ctx) {
+    using PL = Pool<F, NRRT_POOL_NS>;
+    PoolPlan best;
+    best.cap = std::min<uint32_t>(NRRT_STACK_CAP, (std::max<uint32_t>(ctx->max_stack, 4u) + 3u) & ~3u);
+    best.cold_bytes_per_slot = PL::cold_bytes_per_slot();
+    const size_t bpw = PL::bytes_per_warp(best.cap);
+    unsigned best_warps = 0;
+    unsigned force = 0;
+    if (const char* e = std::getenv("NRRT_POOL_WPB")) force = (unsigned)std::atoi(e);  // developer override
+    for (unsigned wpb = NRRT_POOL_WARPS; wpb >= 1; --wpb) {
+        if (force && wpb != force) continue;
+        const size_t smem = wpb * bpw;
+        if (smem > ctx->smem_per_block) continue;
+        if (cudaFuncSetAttribute(k_render_pool<F, NRRT_POOL_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            continue;
+        int blocks = 0;  // resident blocks per SM: shared memory AND registers
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_render_pool<F, NRRT_POOL_NS>, (int)wpb * 32, smem) != cudaSuccess)
+            continue;
+        if ((unsigned)blocks * wpb > best_warps) {
+            best_warps = (unsigned)blocks * wpb;
+            best.warps_per_block = wpb, best.blocks_per_sm = (unsigned)blocks, best.smem = smem;
+        }
+    }
+    (void)cudaGetLastError();
+    best.slots = (uint64_t)ctx->sms * best_warps * NRRT_POOL_NS;
+    return best;
+}
+static PoolPlan pool_plan(const nrrt_ctx* ctx) {
+    switch (ctx->features) {
+        case NRRT_F_CORNELL: return pool_plan_f<NRRT_F_CORNELL>(ctx);
+        case NRRT_F_BALLS: return pool_plan_f<NRRT_F_BALLS>(ctx);
+        case NRRT_F_BALLS_TEX: return pool_plan_f<NRRT_F_BALLS_TEX>(ctx);
+        case NRRT_F_GENERAL: return pool_plan_f<NRRT_F_GENERAL>(ctx);
+        default: return pool_plan_f<NRRT_F_ALL>(ctx);
+    }
+}
+static unsigned pool_blocks(const PoolPlan& pl, uint32_t n_slots) {
+    const unsigned per_block = pl.warps_per_block * NRRT_POOL_NS;
+    return (unsigned)((n_slots + per_block - 1) / per_block);
+}
+static cudaError_t launch_pool(nrrt_ctx* ctx, const PoolPlan& pl, const nrrt_camera& c, const RenderParams& P, double* partials,
+                               double* cold) {
+    if (pl.warps_per_block == 0) return cudaErrorInvalidConfiguration;
+    const unsigned blocks = pool_blocks(pl, P.n_slots);
+    const uint32_t cold_slots = blocks * pl.warps_per_block * NRRT_POOL_NS;
+    cudaError_t e = cudaSuccess;
+#define NRRT_POOL_LAUNCH(FEAT)                                                                                            \
+    e = cudaFuncSetAttribute(k_render_pool<FEAT, NRRT_POOL_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem); \
+    if (e == cudaSuccess)                                                                                                 \
+        k_render_pool<FEAT, NRRT_POOL_NS><<<blocks, pl.warps_per_block * 32, pl.smem, ctx->stream>>>(                     \
+            ctx->dev, c, P, partials, ctx->d_counters, pl.cap, cold, cold_slots);
+    switch (ctx->features) {
+        case NRRT_F_CORNELL: NRRT_POOL_LAUNCH(NRRT_F_CORNELL) break;
+        case NRRT_F_BALLS: NRRT_POOL_LAUNCH(NRRT_F_BALLS) break;
+        case NRRT_F_BALLS_TEX: NRRT_POOL_LAUNCH(NRRT_F_BALLS_TEX) break;
+        case NRRT_F_GENERAL: NRRT_POOL_LAUNCH(NRRT_F_GENERAL) break;
+        default: NRRT_POOL_LAUNCH(NRRT_F_ALL) break;
+    }
+#undef NRRT_POOL_LAUNCH
+    return e;
+}
+}  // extern "C++"
 
 static int ensure_scratch(nrrt_ctx* ctx, size_t bytes) {
     if (ctx->scratch_bytes >= bytes) return NRRT_OK;
@@ -1347,8 +1500,21 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
 
     const bool out_dev = (o.flags & NRRT_RENDER_OUT_DEVICE) != 0;
     const bool counting = (o.flags & NRRT_RENDER_COUNT) != 0;
+    // (instance chains are packed as 16-bit indices in the pooled kernel's slot state: larger scenes use the fused kernel)
+    const bool pooled = o.mode == NRRT_MODE_POOL && !counting && ctx->dev.n_instances <= 65536u;
+    if (o.mode == NRRT_MODE_POOL && !counting && !pooled) o.mode = NRRT_MODE_FUSED;
     const bool wavefront = o.mode == NRRT_MODE_WAVEFRONT && !counting;
     const bool fused = o.mode == NRRT_MODE_FUSED && !counting;
+
+    PoolPlan plan;
+    if (pooled) {  // persistent: every resident pool slot starts with one item; the work counter hands out the rest
+        plan = pool_plan(ctx);
+        if (plan.warps_per_block == 0) {
+            ctx->err = "pooled kernel: the slot pool does not fit in shared memory";
+            return NRRT_ERR_LIMIT;
+        }
+        P.n_slots = (uint32_t)std::min<uint64_t>(n_items64, o.max_slots ? std::min<uint64_t>(o.max_slots, plan.slots) : plan.slots);
+    }
     if (fused) {  // persistent: one thread per resident lane; the work counter hands out the rest
         const uint64_t resident = (uint64_t)(ctx->persistent_blocks / NRRT_EXTEND_MINBLOCKS) * NRRT_FUSED_BLOCKS_PER_SM * NRRT_BLOCK;
         P.n_slots = (uint32_t)std::min<uint64_t>(n_items64, o.max_slots ? std::min<uint64_t>(o.max_slots, resident) : resident);
@@ -1364,6 +1530,11 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     };
     size_t o_fb = out_dev ? 0 : carve(fb_bytes);
     size_t o_part = carve((size_t)P.n_items * 3 * sizeof(double));
+    size_t o_cold = 0;
+    if (pooled) {
+        const size_t cold_slots = (size_t)pool_blocks(plan, P.n_slots) * plan.warps_per_block * NRRT_POOL_NS;
+        o_cold = carve(cold_slots * plan.cold_bytes_per_slot);
+    }
     size_t o_ray = 0, o_T = 0, o_sum = 0, o_attr = 0, o_item = 0, o_sample = 0, o_bounce = 0, o_ht = 0, o_hp = 0, o_hi = 0,
            o_q0 = 0, o_q1 = 0, o_cnt = 0;
     if (wavefront) {
@@ -1398,6 +1569,10 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     if (n == 0 || c.ray_max_bounces == 0) {
         // nothing owned, or every path returns black at depth 0 (camera.rs:276-278)
         if (P.n_items) CK(cudaMemsetAsync(d_part, 0, (size_t)P.n_items * 3 * sizeof(double), ctx->stream));
+    } else if (pooled) {
+        CK(launch_pool(ctx, plan, c, P, d_part, (double*)(base + o_cold)));
+        CK(cudaGetLastError());
+        ++launches;
     } else if (fused) {
         CK(launch_fused(ctx, work_blocks, c, P, d_part));
         CK(cudaGetLastError());

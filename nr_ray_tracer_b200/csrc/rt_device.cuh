@@ -43,6 +43,12 @@ struct DevScene {
     const float4* wnodes;  // four-slot nodes (nrrt_wnode), 8 x float4 each
     const nrrt_box* wide_boxes;  // [8 * n]: own box / gate box per slot
     uint32_t root;         // wide ref
+    // the same trees in binary form (nrrt_node), uploaded only for small scenes: a tree of a dozen nodes gains nothing
+    // from folding levels, and the two-box visit is half the instructions of the four-box one
+    const float4* bnodes;  // 4 x float4 per node, or nullptr
+    const nrrt_box* bchild_boxes;
+    const uint32_t* inst_binner;  // per instance: inner as a binary ref
+    uint32_t broot;
     nrrt_box root_box;
     const double* sphere_rec;  // [n][4]: center xyz, radius
     const double* sphere_speed;  // [n][3] or nullptr when no sphere moves
@@ -75,7 +81,13 @@ __device__ __forceinline__ d3 ld3(const double* p) { return d3{p[0], p[1], p[2]}
 __device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+// (measured on B200: out-of-line copies of the division / square root / Philox sequences shrink the kernels by 10 %
+// but cost 5-15 % throughput — calls force live f64 state through the stack — so they stay inline)
+#ifndef NRRT_DIV_INLINE
+#define NRRT_DIV_INLINE __forceinline__
+#endif
+__device__ NRRT_DIV_INLINE double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ NRRT_DIV_INLINE double xsqrt(double a) { return __dsqrt_rn(a); }
 __device__ __forceinline__ d3 add3(d3 a, d3 b) { return d3{xadd(a.x, b.x), xadd(a.y, b.y), xadd(a.z, b.z)}; }
 __device__ __forceinline__ d3 sub3(d3 a, d3 b) { return d3{xsub(a.x, b.x), xsub(a.y, b.y), xsub(a.z, b.z)}; }
 __device__ __forceinline__ d3 neg3(d3 a) { return d3{-a.x, -a.y, -a.z}; }
@@ -91,7 +103,7 @@ __device__ __forceinline__ d3 cross3(d3 a, d3 b) {
               xsub(xmul(a.x, b.y), xmul(b.x, a.y))};
 }
 // glam normalize: v * (1/sqrt(v.v))
-__device__ __forceinline__ d3 normalize3(d3 a) { return scale3(a, xdiv(1.0, __dsqrt_rn(dot3(a, a)))); }
+__device__ __forceinline__ d3 normalize3(d3 a) { return scale3(a, xdiv(1.0, xsqrt(dot3(a, a)))); }
 // ray.at(t) = origin + t*direction (ray.rs:40-42)
 __device__ __forceinline__ d3 ray_at(d3 o, d3 d, double t) { return add3(o, scale3(d, t)); }
 // Rust f64::signum
@@ -118,6 +130,27 @@ __device__ __forceinline__ d3 mat4_vector(const double* m, d3 v) {
     d3 r = scale3(ld3(m), v.x);
     r = add3(scale3(ld3(m + 3), v.y), r);
     r = add3(scale3(ld3(m + 6), v.z), r);
+    return r;
+}
+
+// 256-bit read-only global load (sm_100: LDG.E.256): one request fetches a 32-byte sector per lane, so a 128-byte
+// node or plane record costs a diverged warp 4 trips through the L1 pipeline instead of 8.  p must be 32-byte aligned.
+struct __align__(32) f32x8 {
+    float v[8];
+};
+__device__ __forceinline__ f32x8 ldg256(const void* p) {
+    f32x8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+        : "l"(p));
+    return r;
+}
+struct __align__(32) f64x4 {
+    double v[4];
+};
+__device__ __forceinline__ f64x4 ldg256d(const void* p) {
+    f64x4 r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
     return r;
 }
 
@@ -194,17 +227,16 @@ __device__ __forceinline__ d3 sphere_center(const DevScene& S, uint32_t i, d3 c,
 template <uint32_t F = NRRT_F_ALL>
 __device__ __forceinline__ double sphere_t(const DevScene& S, uint32_t i, d3 o, d3 d, double tmin, double tmax,
                                            double time) {
-    const double2* rec = reinterpret_cast<const double2*>(S.sphere_rec) + 2 * (size_t)i;
-    double2 r0 = __ldg(rec), r1 = __ldg(rec + 1);
-    d3 c = sphere_center<F>(S, i, mk3(r0.x, r0.y, r1.x), time);
-    double r = r1.y;
+    const f64x4 rec = ldg256d(S.sphere_rec + 4 * (size_t)i);
+    d3 c = sphere_center<F>(S, i, mk3(rec.v[0], rec.v[1], rec.v[2]), time);
+    double r = rec.v[3];
     d3 ec = sub3(c, o);
     double a = dot3(d, d);
     double h = dot3(ec, d);
     double cc = xsub(dot3(ec, ec), xmul(r, r));
     double disc = xsub(xmul(h, h), xmul(a, cc));
     if (disc < 0.0) return __longlong_as_double(0x7ff8000000000000LL);
-    double sq = __dsqrt_rn(disc);
+    double sq = xsqrt(disc);
     double t = xdiv(xsub(h, sq), a);
     if (tmin < t && t < tmax) return t;  // Interval::surrounds
     t = xdiv(xadd(h, sq), a);
@@ -218,17 +250,17 @@ __device__ __forceinline__ double sphere_t(const DevScene& S, uint32_t i, d3 o, 
 __device__ __forceinline__ double plane_t(const DevScene& S, uint32_t i, d3 o, d3 d, double tmin, double tmax,
                                           double tbest, double* alpha_out, double* beta_out, d3* point_out) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    const double2* rec = reinterpret_cast<const double2*>(S.plane_rec) + 8 * (size_t)i;
-    double2 q0 = __ldg(rec), q1 = __ldg(rec + 1);  // normal xyz, d
-    d3 n = mk3(q0.x, q0.y, q1.x);
+    const double* rec = S.plane_rec + 16 * (size_t)i;
+    const f64x4 q0 = ldg256d(rec);  // normal xyz, d
+    d3 n = mk3(q0.v[0], q0.v[1], q0.v[2]);
     double denom = dot3(n, d);
     if (fabs(denom) < 1e-8) return nan;
-    double t = xdiv(xsub(q1.y, dot3(n, o)), denom);
+    double t = xdiv(xsub(q0.v[3], dot3(n, o)), denom);
     if (!(tmin <= t && t <= tmax)) return nan;  // Interval::contains
     if (t > tbest) return nan;
-    double2 q2 = __ldg(rec + 2), q3 = __ldg(rec + 3), q4 = __ldg(rec + 4), q5 = __ldg(rec + 5), q6 = __ldg(rec + 6),
-            q7 = __ldg(rec + 7);
-    d3 pp = mk3(q2.x, q2.y, q3.x), w = mk3(q3.y, q4.x, q4.y), uu = mk3(q5.x, q5.y, q6.x), vv = mk3(q6.y, q7.x, q7.y);
+    const f64x4 q1 = ldg256d(rec + 4), q2 = ldg256d(rec + 8), q3 = ldg256d(rec + 12);
+    d3 pp = mk3(q1.v[0], q1.v[1], q1.v[2]), w = mk3(q1.v[3], q2.v[0], q2.v[1]), uu = mk3(q2.v[2], q2.v[3], q3.v[0]),
+       vv = mk3(q3.v[1], q3.v[2], q3.v[3]);
     d3 point = ray_at(o, d, t);
     d3 q = sub3(point, pp);
     double alpha = dot3(w, cross3(q, vv));
@@ -369,11 +401,11 @@ __device__ __forceinline__ uint32_t wide_visit(const DevScene& S, const Ray32& r
                                                float tcull, uint32_t ni, double tmin, double tmax, LoadRay&& load_exact_ray,
                                                TraceCounters* cnt, uint32_t (&out)[4]) {
     const float4* np = S.wnodes + 8 * (size_t)ni;
-    const float4 LX = __ldg(np), LY = __ldg(np + 1), LZ = __ldg(np + 2), HX = __ldg(np + 3), HY = __ldg(np + 4),
-                 HZ = __ldg(np + 5);
+    const f32x8 A = ldg256(np), B = ldg256(np + 2), C = ldg256(np + 4);  // lo x,y | lo z, hi x | hi y,z
     const uint4 CH = __ldg(reinterpret_cast<const uint4*>(np + 6));
-    const float lx[4] = {LX.x, LX.y, LX.z, LX.w}, ly[4] = {LY.x, LY.y, LY.z, LY.w}, lz[4] = {LZ.x, LZ.y, LZ.z, LZ.w};
-    const float hx[4] = {HX.x, HX.y, HX.z, HX.w}, hy[4] = {HY.x, HY.y, HY.z, HY.w}, hz[4] = {HZ.x, HZ.y, HZ.z, HZ.w};
+    const float lx[4] = {A.v[0], A.v[1], A.v[2], A.v[3]}, ly[4] = {A.v[4], A.v[5], A.v[6], A.v[7]};
+    const float lz[4] = {B.v[0], B.v[1], B.v[2], B.v[3]}, hx[4] = {B.v[4], B.v[5], B.v[6], B.v[7]};
+    const float hy[4] = {C.v[0], C.v[1], C.v[2], C.v[3]}, hz[4] = {C.v[4], C.v[5], C.v[6], C.v[7]};
     const uint32_t ch[4] = {CH.x, CH.y, CH.z, CH.w};
     if (COUNT) cnt->nodes++;
     float e[4], m[4];
@@ -393,20 +425,31 @@ __device__ __forceinline__ uint32_t wide_visit(const DevScene& S, const Ray32& r
         const uint32_t me[4] = {ME.x, ME.y, ME.z, ME.w};
         d3 o, d;
         load_exact_ray(o, d);
+        // (a rolled loop over bit masks: one copy of the call sequence; the slot arrays stay in registers)
+        uint32_t amb_mask = 0, ok_mask = 0, gate_mask = 0, node_mask = 0;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            if (!amb[s]) continue;
+            amb_mask |= amb[s] ? 1u << s : 0u;
+            gate_mask |= (me[s] & NRRT_WNODE_GATED) ? 1u << s : 0u;
+            node_mask |= NRRT_REF_TYPE(ch[s]) == NRRT_REF_NODE ? 1u << s : 0u;
+        }
+#pragma unroll 1
+        for (uint32_t s = 0; s < 4; ++s) {
+            if (!((amb_mask >> s) & 1u)) continue;
             bool ok = true;
-            if (me[s] & NRRT_WNODE_GATED) {
+            if ((gate_mask >> s) & 1u) {
                 if (COUNT) cnt->exact++;
                 ok = box_hit_exact(S.wide_boxes + 8 * (size_t)ni + 2 * s + 1, o, d, tmin, tmax);
             }
-            if (ok && NRRT_REF_TYPE(ch[s]) == NRRT_REF_NODE) {
+            if (ok && ((node_mask >> s) & 1u)) {
                 if (COUNT) cnt->exact++;
                 ok = box_hit_exact(S.wide_boxes + 8 * (size_t)ni + 2 * s, o, d, tmin, tmax);
             }
-            v[s] = ok;
+            ok_mask |= ok ? 1u << s : 0u;
         }
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            if (amb[s]) v[s] = (ok_mask >> s) & 1u;
     }
     uint32_t k[4], n = 0;
 #pragma unroll
@@ -485,7 +528,8 @@ struct MemCtx {
 //   SPEC: speculative traversal: a lane that reaches a primitive leaf parks it and keeps walking inner nodes while
 //         other lanes of its warp are still in the node loop, instead of idling.  Pays on deep trees (teapot +16 %,
 //         sphere field +7 %), costs on tiny ones (Cornell, 17 nodes: -4 %), so the render path selects it by tree size.
-template <bool VISIT_ALL, bool COUNT, uint32_t F = NRRT_F_ALL, bool SPEC = false>
+//   WIDE: walk the four-slot nodes (default) or the binary ones (small trees; needs DevScene::bnodes)
+template <bool VISIT_ALL, bool COUNT, uint32_t F = NRRT_F_ALL, bool SPEC = false, bool WIDE = true>
 struct Traversal {
     d3 o, d;         // ray in the current space (world, or the object space of the innermost entered instance)
     Ray32 r32;
@@ -532,6 +576,58 @@ struct Traversal {
         }
     }
 
+    // one visit of a binary node (nrrt_node): both children's boxes, near child first
+    template <class Ctx>
+    __device__ __forceinline__ void binary_step(const DevScene& S, const Ctx& ctx, double tmin, double tmax, float tmin32,
+                                                float tmax32, uint32_t* stack, uint32_t sstride, TraceCounters* cnt) {
+        const uint32_t ni = NRRT_REF_INDEX(cur);
+        const float4* np = S.bnodes + 4 * (size_t)ni;
+        const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+        // layout: lo[0].xyz lo[1].xyz | hi[0].xyz hi[1].xyz | child[0] child[1] pad pad
+        const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+        if (COUNT) cnt->nodes++;
+        float e0, g0, m0, e1, g1, m1;
+        box_filter(r32, n0.x, n0.y, n0.z, n1.z, n1.w, n2.x, tmin32, tmax32, e0, g0, m0);
+        box_filter(r32, n0.w, n1.x, n1.y, n2.y, n2.z, n2.w, tmin32, tmax32, e1, g1, m1);
+        // leaves are not box-tested by the reference (object.rs:95-97): visit unless certainly missed;
+        // inner children must pass the reference's test: certain from the filter, else exact
+        bool v0 = (c0 != NRRT_REF_NONE) && !(g0 < -m0);
+        bool v1 = (c1 != NRRT_REF_NONE) && !(g1 < -m1);
+        const bool amb0 = v0 && NRRT_REF_TYPE(c0) == NRRT_REF_NODE && !(g0 >= m0);
+        const bool amb1 = v1 && NRRT_REF_TYPE(c1) == NRRT_REF_NODE && !(g1 >= m1);
+        if (amb0 || amb1) {  // rare
+            d3 o, d;
+            load_ray(ctx, o, d);
+            if (amb0) {
+                if (COUNT) cnt->exact++;
+                v0 = box_hit_exact(S.bchild_boxes + 2 * (size_t)ni, o, d, tmin, tmax);
+            }
+            if (amb1) {
+                if (COUNT) cnt->exact++;
+                v1 = box_hit_exact(S.bchild_boxes + 2 * (size_t)ni + 1, o, d, tmin, tmax);
+            }
+        }
+        if (!VISIT_ALL) {
+            // prune children that start certainly behind the best hit (ties are kept: margin > 0)
+            v0 = v0 && !(e0 - m0 > tcull);
+            v1 = v1 && !(e1 - m1 > tcull);
+        }
+        if (v0 && v1) {
+            const bool swap = !VISIT_ALL && (e1 < e0);
+            stack[sp * sstride] = swap ? c0 : c1;
+            ++sp;
+            cur = swap ? c1 : c0;
+        } else if (v0 || v1) {
+            cur = v0 ? c0 : c1;
+        } else {
+            cur = NRRT_REF_NONE;
+            if (sp) {
+                --sp;
+                cur = stack[sp * sstride];
+            }
+        }
+    }
+
     // filter bounds of the query range; the margins cover the rounding
     static __device__ __forceinline__ float lo32(double tmin) { return (float)tmin; }
     static __device__ __forceinline__ float hi32(double tmax) { return (tmax < 3.0e38) ? (float)tmax : 3.4e38f; }
@@ -553,7 +649,7 @@ struct Traversal {
         tcull = 3.4e38f;                                    // f32 upper bound of best.t (+ slack)
         sp = 0;
         pend = NRRT_REF_NONE;
-        cur = S.root;
+        cur = WIDE ? S.root : S.broot;
         // root of the scene: an inner node tests its own box (object.rs:102)
         if (NRRT_REF_TYPE(cur) == NRRT_REF_NODE) {
             if (!root_box_test<COUNT>(&S.root_box, r32, wo, wd, tmin, tmax, tmin32, tmax32, cnt)) cur = NRRT_REF_NONE;
@@ -584,6 +680,11 @@ struct Traversal {
             if (!at_node) {
                 if (kSpeculate) continue;
                 break;
+            }
+            if (!WIDE) {
+                binary_step(S, ctx, tmin, tmax, tmin32, tmax32, stack, sstride, cnt);
+                postpone_leaf(has, stack, sstride);
+                continue;
             }
             uint32_t nxt[4];
             const uint32_t n = wide_visit<VISIT_ALL, COUNT>(
@@ -667,7 +768,7 @@ struct Traversal {
             // enter an instance: transform the ray (exactly, wrapper by wrapper), test the nested root's box
             uint32_t ii = NRRT_REF_INDEX(cur);
             const nrrt_instance* in = &S.instances[ii];
-            uint32_t inner = in->inner;
+            uint32_t inner = WIDE ? in->inner : S.inst_binner[ii];
             if (inner != NRRT_REF_NONE && level < NRRT_MAX_INSTANCE_DEPTH) {
                 d3 no = o, nd = d;
                 if (COUNT) cnt->inst++;
@@ -1020,7 +1121,7 @@ __device__ __forceinline__ bool shade_hit(const DevScene& S, const HitRec& h, d3
         double ri = h.front_face ? xdiv(1.0, m->param) : m->param;
         d3 unit = normalize3(rd);
         double cos_theta = fmin(dot3(neg3(unit), h.normal), 1.0);
-        double sin_theta = __dsqrt_rn(xsub(1.0, xmul(cos_theta, cos_theta)));
+        double sin_theta = xsqrt(xsub(1.0, xmul(cos_theta, cos_theta)));
         bool refl = xmul(ri, sin_theta) > 1.0;
         if (!refl) {
             double r0 = xdiv(xsub(1.0, ri), xadd(1.0, ri));  // reflectance :13-19
@@ -1037,7 +1138,7 @@ __device__ __forceinline__ bool shade_hit(const DevScene& S, const HitRec& h, d3
             double ndi = dot3(h.normal, unit);
             double k = xsub(1.0, xmul(xmul(ri, ri), xsub(1.0, xmul(ndi, ndi))));
             if (k >= 0.0)
-                new_dir = sub3(scale3(unit, ri), scale3(h.normal, xadd(xmul(ri, ndi), __dsqrt_rn(k))));
+                new_dir = sub3(scale3(unit, ri), scale3(h.normal, xadd(xmul(ri, ndi), xsqrt(k))));
             else
                 new_dir = mk3(0.0, 0.0, 0.0);
         }

@@ -18,7 +18,8 @@ from tests.scenes_util import ALL_SCENES, BASELINE_SCENES, load
 
 pytestmark = pytest.mark.gpu
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
-MODES = [(A.MODE_WAVEFRONT, "wavefront"), (A.MODE_MEGAKERNEL, "megakernel"), (A.MODE_FUSED, "fused")]
+MODES = [(A.MODE_WAVEFRONT, "wavefront"), (A.MODE_MEGAKERNEL, "megakernel"), (A.MODE_FUSED, "fused"),
+         (A.MODE_POOL, "pool")]
 
 
 def _scene(ctx, g):
@@ -153,7 +154,7 @@ def test_render_same_streams_matches_oracle(gpu_ctx, name):
         assert abs(float(img.mean()) - float(ref.mean())) <= 0.01 * float(ref.mean()) + 1e-6
         imgs.append(img)
     # the kernel designs share device functions, work items and streams: identical images
-    assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])
+    assert all(np.array_equal(imgs[0], im) for im in imgs[1:])
     del hs
 
 
@@ -388,7 +389,7 @@ def test_moving_spheres_match_oracle(gpu_ctx, with_planes):
         assert float((rel <= 1e-5).all(axis=2).mean()) >= 0.99, mname
         assert abs(st["segments"] - cnt["segments"]) <= 0.005 * cnt["segments"] + 2
         imgs.append(img)
-    assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])
+    assert all(np.array_equal(imgs[0], im) for im in imgs[1:])
     del hs
 
 
@@ -422,7 +423,7 @@ def test_sah_bvh_option_gives_the_reference_result(gpu_ctx, name):
         gpu, st = gpu_ctx.trace_rays(rays)
         res = kat.compare_hits(gpu, ref)
         imgs = [gpu_ctx.render(cam, seed=21, mode=mode)[0] for mode, _ in MODES]
-        assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])
+        assert all(np.array_equal(imgs[0], im) for im in imgs[1:])
         out[bvh] = (res, st, imgs[0])
         del hs
     assert kat.hits_ok(out["reference"][0])
@@ -521,7 +522,7 @@ def test_textured_sphere_field_deep_tree(gpu_ctx):
         assert float((rel <= 1e-5).all(axis=2).mean()) >= 0.99, mname
         assert abs(st["segments"] - cnt["segments"]) <= 0.005 * cnt["segments"] + 2
         imgs.append(img)
-    assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])
+    assert all(np.array_equal(imgs[0], im) for im in imgs[1:])
     del hs
 
 

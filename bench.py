@@ -165,12 +165,29 @@ def run_reference(args):
 # ----------------------------------------------------------------------------- B200 arm
 def scene_h2d_bytes(desc) -> int:
     d = desc
-    b = d.n_nodes * 64 + d.n_nodes * 2 * 48
+    b = d.n_wnodes * 128 + d.n_wnodes * 8 * 48 + (d.n_nodes * (64 + 96) if d.n_nodes < 64 else 0)
     b += d.n_spheres * (32 + 3 * 4) + d.n_planes * (128 + 3 * 4)
     b += d.n_instances * (64 + 4) + d.n_xforms * 200 + d.n_materials * 16 + d.n_textures * 72
     for i in range(d.n_images):
         b += d.images[i].width * d.images[i].height * 4
     return int(b)
+
+
+def primary_rays(cam, min_rays=2_000_000):
+    """Coherent camera rays of `cam` (pixel centres, no lens), supersampled on a regular sub-pixel grid until there
+    are at least min_rays of them: the input of the traversal-only microbenchmark."""
+    W, H = cam.width, cam.height
+    k = 1
+    while W * H * k * k < min_rays:
+        k += 1
+    sub = (np.arange(k, dtype=np.float64) + 0.5) / k - 0.5
+    xs = (np.arange(W, dtype=np.float64)[:, None] + sub[None, :]).reshape(-1)
+    ys = (np.arange(H, dtype=np.float64)[:, None] + sub[None, :]).reshape(-1)
+    gx, gy = np.meshgrid(xs, ys)
+    tl, du, dv = (np.array(list(v)) for v in (cam.viewport_top_left, cam.pixel_delta_u, cam.pixel_delta_v))
+    org = np.array(list(cam.look_from))
+    pts = tl + gx[..., None] * du + gy[..., None] * dv
+    return np.ascontiguousarray(np.concatenate([np.broadcast_to(org, pts.shape), pts - org], axis=-1).reshape(-1, 6))
 
 
 def run_b200(args):
@@ -188,9 +205,11 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    mode = {"fused": A.MODE_FUSED, "wavefront": A.MODE_WAVEFRONT, "megakernel": A.MODE_MEGAKERNEL}[args.mode]
-    kernel_name = {"fused": "k_render_fused", "wavefront": "k_wf_extend", "megakernel": "k_render_mega"}[args.mode]
-    R = D.DEFAULT_ROWS_PER_BLOCK
+    mode = {"auto": A.MODE_AUTO, "pool": A.MODE_POOL, "fused": A.MODE_FUSED, "wavefront": A.MODE_WAVEFRONT,
+            "megakernel": A.MODE_MEGAKERNEL}[args.mode]
+    KERNEL = {A.MODE_POOL: "k_render_pool", A.MODE_FUSED: "k_render_fused", A.MODE_WAVEFRONT: "k_wf_extend",
+              A.MODE_MEGAKERNEL: "k_render_mega"}
+    R = D.rows_per_block_for(world)
 
     graph = load_scene(SCENE, camera_override=CameraConfig(width=args.width, height=args.height,
                                                            samples_per_pixel=args.spp, ray_max_bounces=DEPTH))
@@ -200,8 +219,9 @@ def run_b200(args):
     host = api.HostScene(graph, bvh=args.bvh)
     ctx.upload(host)
     W, H = cam.width, cam.height
-    fb = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    G = D.FramebufferGather(H, W, rank, world, R, dev)      # persistent buffers of the multi-GPU exchange
     pinned = torch.zeros((H, W, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+    pageable = np.zeros((H, W, 3), dtype=np.float32) if rank == 0 else None
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -211,22 +231,18 @@ def run_b200(args):
 
     def step_device():
         """value: scene resident, result left on the device (rank 0 holds the assembled image)."""
-        _, st = ctx.render(cam, seed=0, mode=mode, rank=rank, world=world, rows_per_block=R,
-                           out_device_ptr=fb.data_ptr())
-        if world > 1:
-            D.gather_framebuffer(fb, rank, world, R)
+        _, st, _ = D.render_distributed(ctx, cam, rank, world, seed=0, mode=mode, gather=G)
         return st
 
-    def step_e2e():
-        """e2e: the public API call — host scene description in, host image out."""
-        h = api.HostScene(graph, bvh=args.bvh)   # BVH build + flatten (host)
-        ctx.upload(h)                    # H2D of the flat scene
-        _, st = ctx.render(cam, seed=0, mode=mode, rank=rank, world=world, rows_per_block=R,
-                           out_device_ptr=fb.data_ptr())
-        full = D.gather_framebuffer(fb, rank, world, R) if world > 1 else fb
-        if rank == 0:
-            pinned.copy_(full, non_blocking=True)   # D2H of the result
-            torch.cuda.current_stream().synchronize()
+    def step_e2e(out_np=None):
+        """e2e: the call a user makes — Scene(...).render(): host scene description in (BVH build + flatten on the
+        host, H2D upload of the flat scene), host f32 image out (D2H inside nrrt_render).  N > 1: the same per rank
+        through distributed.render_distributed (render -> NCCL gather -> D2H on rank 0)."""
+        scene = api.Scene(graph, ctx=ctx, bvh=args.bvh)
+        if world == 1:
+            scene.render(out=out_np, seed=0, mode=mode)
+            return scene.last_stats
+        _, st, _ = D.render_distributed(ctx, scene.camera, rank, world, seed=0, mode=mode, gather=G, host_out=pinned)
         return st
 
     def timed(fn, k):
@@ -254,6 +270,20 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # ---- untimed: the N-GPU image must be the 1-GPU image, bit for bit (low spp, once)
+    identical = None
+    if world > 1:
+        ccam = api.camera_build(graph.camera.to_builder_config())
+        ccam.samples_per_pixel = min(4, cam.samples_per_pixel)
+        full, _, _ = D.render_distributed(ctx, ccam, rank, world, seed=0, mode=mode, gather=G)
+        if rank == 0:
+            one = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+            ctx.render(ccam, seed=0, mode=mode, out_device_ptr=one.data_ptr())
+            torch.cuda.synchronize()
+            identical = bool(torch.equal(full, one))
+            del one
+        barrier()
+
     # ---- warm-up
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -276,80 +306,88 @@ def run_b200(args):
     ext_ms = sum(s["extend_ms"] for s in stats)
     ext_launches = sum(s["extend_launches"] for s in stats)
     my_segs = sum(s["segments"] for s in stats)
+    mode_used = stats[0]["mode"]
+    kernel_name = KERNEL.get(mode_used, "?")
 
     # ---- timed: end to end through the public API (host buffers)
-    step_e2e()
-    ms_e2e, stats_e2e = timed(step_e2e, args.steps)
+    pinned_np = pinned.numpy() if rank == 0 else None
+    step_e2e(pinned_np)
+    ms_e2e, stats_e2e = timed(lambda: step_e2e(pinned_np), args.steps)
     segs_e2e = total(stats_e2e, "segments")
     e2e_value = segs_e2e / (sum(ms_e2e) * 1e-3) / 1e6
+    e2e_pageable = None
+    if world == 1:
+        ms_pg, stats_pg = timed(lambda: step_e2e(pageable), args.steps)
+        e2e_pageable = total(stats_pg, "segments") / (sum(ms_pg) * 1e-3) / 1e6
 
     line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (traverse/intersect): algorithmic bytes per segment from an
-        # instrumented low-spp pass over the same scene/camera (untimed), SURVEY.md §8(d)
+        # ---- per-segment traversal counts from an instrumented low-spp pass over the same scene/camera (untimed)
         ccam = api.camera_build(graph.camera.to_builder_config())
         ccam.samples_per_pixel = 2
         ctx.upload(host)
+        fb = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
         _, cst = ctx.render(ccam, seed=0, count=True, out_device_ptr=fb.data_ptr())
+        del fb
         nodes_seg = cst["node_visits"] / cst["segments"]
         prims_seg = cst["prim_tests"] / cst["segments"]
         exact_seg = cst["box_exact"] / cst["segments"]
         d = host.desc
         b_prim = 128 if d.n_planes >= d.n_spheres else 32   # bytes one exact primitive test reads (one record)
-        b_state = 48 + 24 + 4 if mode == A.MODE_WAVEFRONT else 0  # extend kernel: ray in, hit out, queue index
-        bytes_seg = nodes_seg * 64 + exact_seg * 48 + prims_seg * b_prim + b_state
-        # traversal-only microbenchmark (north_star's "traversal roofline"): coherent primary rays of the same camera
-        # through the fixed-ray entry point, no shading, no path state
-        Wc, Hc = cam.width, cam.height
-        xs, ys = np.meshgrid(np.arange(Wc, dtype=np.float64), np.arange(Hc, dtype=np.float64))
-        tl, du, dv = (np.array(list(v)) for v in (cam.viewport_top_left, cam.pixel_delta_u, cam.pixel_delta_v))
-        org = np.array(list(cam.look_from))
-        pts = tl + xs[..., None] * du + ys[..., None] * dv
-        prim_rays = torch.from_numpy(np.ascontiguousarray(
-            np.concatenate([np.broadcast_to(org, pts.shape), pts - org], axis=-1).reshape(-1, 6))).to(dev)
-        prim_hits = torch.zeros((prim_rays.shape[0], 112), dtype=torch.uint8, device=dev)
+        b_state = 48 + 24 + 4 if mode_used == A.MODE_WAVEFRONT else 0  # extend kernel: ray in, hit out, queue index
+        bytes_seg = nodes_seg * 128 + exact_seg * 48 + prims_seg * b_prim + b_state   # four-slot nodes: 128 B each
+        # ---- the traversal ceiling, measured here: coherent primary rays of the same camera (>= 2 M of them) through
+        # the closest-hit entry point of the same library — same BVH, same box filter and exact primitive tests, no
+        # shading, no path state, 16 bytes out per ray
+        prim_rays = torch.from_numpy(primary_rays(cam)).to(dev)
+        n_rays = prim_rays.shape[0]
+        prim_hits = torch.zeros((n_rays, 16), dtype=torch.uint8, device=dev)
         trav_best = 0.0
-        for _ in range(5):
-            ts = ctx.trace_rays_device(prim_rays.data_ptr(), prim_rays.shape[0], prim_hits.data_ptr())
-            trav_best = max(trav_best, prim_rays.shape[0] / ts["kernel_ms"] / 1e3)
+        for _ in range(6):
+            ts = ctx.trace_rays_device(prim_rays.data_ptr(), n_rays, prim_hits.data_ptr(), compact=True)
+            trav_best = max(trav_best, n_rays / ts["kernel_ms"] / 1e3)
         del prim_rays, prim_hits
-        extend_rate = (my_segs / (ext_ms * 1e-3) / 1e6) if ext_ms > 0 else None
+        kernel_rate = (my_segs / (ext_ms * 1e-3) / 1e6) if ext_ms > 0 else None
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except (OSError, ValueError):
             pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = (my_segs * bytes_seg) / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else None
-        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per segment there, scaled to
-        # this run's segments per launch)
-        traffic = issue_pct = lanes = None
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_achieved = (my_segs * bytes_seg) / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else None
+        # ---- ncu figures of the same kernel from ONE --set full capture of this build on this workload
+        # (profiles/ncu_traffic.json names the capture; tools/ncu_traffic.py regenerates it)
+        traffic = issue_pct = lanes = capture = None
         try:
             nt = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             k = nt[kernel_name]
             traffic = k["dram_bytes_per_segment"] * (my_segs / max(ext_launches, 1))
             issue_pct, lanes = k.get("issue_slot_utilisation_pct"), k.get("active_threads_per_instruction")
+            capture = k.get("source")
         except (OSError, ValueError, KeyError):
             pass
         roofline = {
-            "bound": "hbm", "kernel": kernel_name,
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-            "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650",
+            "bound": "issue", "kernel": kernel_name, "kernel_design": A.MODE_NAMES.get(mode_used),
+            "achieved": kernel_rate, "peak": trav_best, "unit": "Mrays/s",
+            "frac": (kernel_rate / trav_best) if kernel_rate and trav_best else None,
+            "peak_source": f"traversal-only microbenchmark measured in this run: {n_rays} coherent primary rays of the same "
+                           "camera through nrrt_trace_rays (NRRT_TRACE_COMPACT: closest hit only, 16 B out per ray), best of 6",
             "traffic": traffic,
-            "traffic_source": "profiles/ncu_traffic.json (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per "
-                              "segment of the same kernel) x segments per launch of this run",
-            "algorithmic_bytes_per_launch": bytes_seg * (my_segs / max(ext_launches, 1)),
+            "traffic_source": f"profiles/ncu_traffic.json <- {capture}: dram__bytes_read.sum + dram__bytes_write.sum per "
+                              "segment of the same kernel x segments per launch of this run",
             "ncu_issue_slot_utilisation_pct": issue_pct, "ncu_active_threads_per_instruction": lanes,
+            "ncu_useful_lane_slot_frac": (issue_pct / 100.0 * lanes / 32.0) if issue_pct and lanes else None,
+            "why_issue": "the scene (KB-MB) lives in L1/L2 and path state in shared memory; DRAM sees only the per-item partial "
+                         "sums, so the binding limit is warp-instruction issue x lanes active per instruction, not HBM",
+            "hbm": {"algorithmic_gbs": hbm_achieved, "peak_gbs": hbm_peak,
+                    "frac": (hbm_achieved / hbm_peak) if hbm_achieved else None,
+                    "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650",
+                    "note": "algorithmic node/primitive bytes are served by L1/L2, not HBM; reported for scale only"},
+            "algorithmic_bytes_per_launch": bytes_seg * (my_segs / max(ext_launches, 1)),
             "bytes_per_segment": bytes_seg, "nodes_per_segment": nodes_seg, "prims_per_segment": prims_seg,
             "exact_box_tests_per_segment": exact_seg, "segments_per_launch": my_segs / max(ext_launches, 1),
             "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": ext_launches,
             "kernel_share_of_step": ext_ms / sum_ms,
-            "extend_kernel_mrays_s": extend_rate,
-            "traversal_microbench_mrays_s": trav_best,
-            "frac_of_traversal_microbench": (extend_rate / trav_best) if extend_rate and trav_best else None,
-            "traversal_microbench": "coherent primary rays of the same camera through nrrt_trace_rays (no shading)",
-            "note": "node/primitive fetches are L1/L2-resident by design (scene is KB-MB); the binding limit is "
-                    "SM issue + FP64 pipe, see profiles/ for the ncu issue-slot figures",
         }
         # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
         cpu = None
@@ -363,25 +401,35 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": sum_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{SCENE} {args.width}x{args.height} {args.spp}spp depth{DEPTH}",
-                       "kernel_design": args.mode, "bvh": args.bvh, "partition": f"row-blocks of {R}, round-robin over {world} GPU(s)",
+                       "kernel_design": A.MODE_NAMES.get(mode_used), "requested_mode": args.mode, "bvh": args.bvh,
+                       "partition": f"row-blocks of {R}, round-robin over {world} GPU(s)",
                        "l2": "flushed between timed steps (256 MB write); the scene (KB-MB) is cache-resident by design, path "
-                             "state lives in shared memory (fused) or streams through HBM (wavefront)",
+                             "state lives in shared memory",
                        "rng": "Philox4x32-10, seed 0"},
             "time_to_image_s": sum_ms / args.steps / 1e3,
             "segments_per_step": segs / args.steps, "paths_per_step": paths / args.steps,
             "segments_per_path": segs / max(paths, 1),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": scene_h2d_bytes(host.desc),
-                    "d2h_bytes_per_step": W * H * 3 * 4, "ms_per_step": sum(ms_e2e) / args.steps},
+                    "d2h_bytes_per_step": W * H * 3 * 4, "ms_per_step": sum(ms_e2e) / args.steps,
+                    "call": "api.Scene(graph).render(out=<pinned host buffer>) — host BVH build + flatten, H2D scene upload, "
+                            "nrrt_render with a host out_rgb (D2H inside)" if world == 1 else
+                            "api.Scene(graph) per rank + distributed.render_distributed(..., host_out=<pinned>) — render, "
+                            "NCCL gather to rank 0, D2H",
+                    "pageable_host_buffer_value": e2e_pageable},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        if identical is not None:
+            line["multi_gpu_image_identical_to_single_gpu"] = identical
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line))
+        if identical is False:
+            return 3
     return 0
 
 
@@ -392,7 +440,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="fused", choices=["fused", "wavefront", "megakernel"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "pool", "fused", "wavefront", "megakernel"],
+                    help="auto = the product path: pooled kernel on deep trees, fused kernel otherwise")
     ap.add_argument("--bvh", default="reference", choices=["reference", "sah"],
                     help="reference = the reference's tree (parity contract, default); sah = opt-in SAH inner nodes")
     ap.add_argument("--scene", default=SCENE, help="scene file (default: the benchmark workload)")

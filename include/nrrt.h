@@ -367,12 +367,21 @@ typedef struct nrrt_hit {
     uint32_t _pad;
 } nrrt_hit;
 
+typedef struct nrrt_hit_compact {
+    double t;      /* +inf on miss */
+    uint32_t prim; /* winning primitive ref (NRRT_REF_NONE on miss) */
+    uint32_t depth_inst0; /* instance levels above the primitive | outermost instance index << 3 */
+} nrrt_hit_compact;
+
 enum {
     NRRT_TRACE_ORDERED = 0,    /* near-first traversal with conservative t-shrinking (render path) */
     NRRT_TRACE_VISIT_ALL = 1,  /* visit exactly the reference's node set (no shrinking)            */
     NRRT_TRACE_HOST_BUFFERS = 0,
     NRRT_TRACE_DEVICE_BUFFERS = 2,
-    NRRT_TRACE_COUNT = 4       /* also fill node_visits / box_exact / prim_tests (per-ray atomics: slower) */
+    NRRT_TRACE_COUNT = 4,      /* also fill node_visits / box_exact / prim_tests (per-ray atomics: slower) */
+    NRRT_TRACE_COMPACT = 8     /* `out` is n x nrrt_hit_compact (16 bytes per ray: t and the winning primitive) instead of
+                                  n x nrrt_hit: the closest-hit query alone, no HitRecord — the traversal-only
+                                  microbenchmark that bench.py reports the render kernels against */
 };
 
 typedef struct nrrt_trace_stats {
@@ -394,9 +403,12 @@ enum nrrt_render_mode {
     NRRT_MODE_MEGAKERNEL = 1, /* one kernel, per-thread path loop, whole state in registers */
     NRRT_MODE_FUSED = 2,      /* persistent warps: traverse with warp-voted in-place shading, path state in
                                  shared memory (no ray / hit-record round trips through HBM)   */
-    NRRT_MODE_POOL = 3        /* persistent warps, each scheduling a pool of path slots held in shared memory:
+    NRRT_MODE_POOL = 3,       /* persistent warps, each scheduling a pool of path slots held in shared memory:
                                  node / primitive / instance / shade stages run on whichever slots are ready,
                                  so every stage runs with (nearly) all 32 lanes                  */
+    NRRT_MODE_AUTO = 4        /* the product path: POOL for scenes with deep trees (meshes), FUSED otherwise —
+                                 whichever measured faster on B200 for that kind of scene; nrrt_render_stats.mode
+                                 reports the design that ran.  All designs give the bit-identical image. */
 };
 
 typedef struct nrrt_render_opts {
@@ -411,7 +423,9 @@ typedef struct nrrt_render_opts {
 enum {
     NRRT_RENDER_OUT_HOST = 0,
     NRRT_RENDER_OUT_DEVICE = 1, /* out_rgb is a device pointer */
-    NRRT_RENDER_COUNT = 2       /* instrumented megakernel: also count node visits / primitive tests (slower) */
+    NRRT_RENDER_COUNT = 2,      /* instrumented megakernel: also count node visits / primitive tests (slower) */
+    NRRT_RENDER_OUT_PACKED = 4  /* out_rgb holds only the rows this rank owns, packed in ascending row order
+                                   (stats.pixels * 3 floats): what a multi-GPU gather sends, without a pack step */
 };
 
 typedef struct nrrt_render_stats {
@@ -422,7 +436,7 @@ typedef struct nrrt_render_stats {
     double extend_ms;      /* share of device_ms in the traverse/intersect kernel (wavefront) */
     uint64_t extend_launches;
     uint32_t pixels;       /* pixels owned by this rank                        */
-    uint32_t _pad;
+    uint32_t mode;         /* nrrt_render_mode that ran (resolves NRRT_MODE_AUTO) */
     uint64_t node_visits;  /* NRRT_RENDER_COUNT only: inner nodes fetched      */
     uint64_t box_exact;    /*   f32-inconclusive / root box tests done in f64  */
     uint64_t prim_tests;   /*   exact primitive tests                          */
@@ -445,9 +459,9 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* camera, const nrrt_render_opts
 int nrrt_encode_rgb8(nrrt_ctx* ctx, const float* rgb, uint32_t width, uint32_t height, float gamma, uint32_t flags,
                      uint8_t* out_rgb8);
 
-/* sizeof() of the ABI structs as compiled (which = 0..17: object, material, texture,
+/* sizeof() of the ABI structs as compiled (which = 0..18: object, material, texture,
  * image, graph_desc, camera_config, camera, node, box, xform, instance, scene_desc, hit, trace_stats,
- * render_opts, render_stats, camera_file, wnode) so a binding can verify its mirror of this header. */
+ * render_opts, render_stats, camera_file, wnode, hit_compact) so a binding can verify its mirror of this header. */
 size_t nrrt_abi_sizeof(int which);
 
 #ifdef __cplusplus

@@ -23,9 +23,10 @@ REF_NONE = 0xFFFFFFFF
 REF_TYPE_SHIFT = 29
 REF_INDEX_MASK = 0x1FFFFFFF
 
-TRACE_ORDERED, TRACE_VISIT_ALL, TRACE_DEVICE_BUFFERS, TRACE_COUNT = 0, 1, 2, 4
-MODE_WAVEFRONT, MODE_MEGAKERNEL, MODE_FUSED, MODE_POOL = 0, 1, 2, 3
-RENDER_OUT_HOST, RENDER_OUT_DEVICE, RENDER_COUNT = 0, 1, 2
+TRACE_ORDERED, TRACE_VISIT_ALL, TRACE_DEVICE_BUFFERS, TRACE_COUNT, TRACE_COMPACT = 0, 1, 2, 4, 8
+MODE_WAVEFRONT, MODE_MEGAKERNEL, MODE_FUSED, MODE_POOL, MODE_AUTO = 0, 1, 2, 3, 4
+MODE_NAMES = {0: "wavefront", 1: "megakernel", 2: "fused", 3: "pool", 4: "auto"}
+RENDER_OUT_HOST, RENDER_OUT_DEVICE, RENDER_COUNT, RENDER_OUT_PACKED = 0, 1, 2, 4
 MAX_INSTANCE_DEPTH = 4
 
 u32, u64, f64, f32 = C.c_uint32, C.c_uint64, C.c_double, C.c_float
@@ -120,6 +121,10 @@ class Hit(C.Structure):
                 ("inst", u32 * MAX_INSTANCE_DEPTH), ("_pad", u32)]
 
 
+class HitCompact(C.Structure):
+    _fields_ = [("t", f64), ("prim", u32), ("depth_inst0", u32)]
+
+
 class TraceStats(C.Structure):
     _fields_ = [("node_visits", u64), ("box_exact", u64), ("prim_tests", u64), ("kernel_ms", f64)]
 
@@ -131,7 +136,7 @@ class RenderOpts(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("paths", u64), ("segments", u64), ("launches", u64), ("device_ms", f64), ("extend_ms", f64),
-                ("extend_launches", u64), ("pixels", u32), ("_pad", u32),
+                ("extend_launches", u64), ("pixels", u32), ("mode", u32),
                 ("node_visits", u64), ("box_exact", u64), ("prim_tests", u64), ("inst_entries", u64),
                 ("inst_misses", u64)]
 

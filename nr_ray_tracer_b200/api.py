@@ -76,7 +76,8 @@ def lib() -> C.CDLL:
 
 
 ABI_STRUCTS = [A.Object, A.Material, A.Texture, A.Image, A.GraphDesc, A.CameraConfig, A.Camera, A.Node, A.Box,
-               A.Xform, A.Instance, A.SceneDesc, A.Hit, A.TraceStats, A.RenderOpts, A.RenderStats, A.CameraFile, A.WNode]
+               A.Xform, A.Instance, A.SceneDesc, A.Hit, A.TraceStats, A.RenderOpts, A.RenderStats, A.CameraFile, A.WNode,
+               A.HitCompact]
 
 
 def camera_build(cfg: A.CameraConfig) -> A.Camera:
@@ -239,24 +240,26 @@ class Context:
                      "kernel_ms": st.kernel_ms}
 
     def trace_rays_device(self, rays_ptr: int, n: int, out_ptr: int, tmin: float = 0.001, tmax: float = float("inf"),
-                          visit_all: bool = False, count: bool = False):
-        """rays_ptr / out_ptr are device pointers (n x 6 f64, n x nrrt_hit)."""
+                          visit_all: bool = False, count: bool = False, compact: bool = False):
+        """rays_ptr / out_ptr are device pointers (n x 6 f64, n x nrrt_hit — or n x 16-byte nrrt_hit_compact with
+        compact=True: the closest-hit query alone, no HitRecord)."""
         st = A.TraceStats()
         flags = (A.TRACE_VISIT_ALL if visit_all else A.TRACE_ORDERED) | A.TRACE_DEVICE_BUFFERS | \
-            (A.TRACE_COUNT if count else 0)
+            (A.TRACE_COUNT if count else 0) | (A.TRACE_COMPACT if compact else 0)
         self._check(lib().nrrt_trace_rays(self._h, C.c_void_p(rays_ptr), n, tmin, tmax, flags, C.c_void_p(out_ptr),
                                           C.byref(st)))
         return {"node_visits": st.node_visits, "box_exact": st.box_exact, "prim_tests": st.prim_tests,
                 "kernel_ms": st.kernel_ms}
 
-    def render(self, cam: A.Camera, out: Optional[np.ndarray] = None, seed: int = 0, mode: int = A.MODE_FUSED,
+    def render(self, cam: A.Camera, out: Optional[np.ndarray] = None, seed: int = 0, mode: int = A.MODE_AUTO,
                rank: int = 0, world: int = 1, rows_per_block: int = 0, max_slots: int = 0,
                out_device_ptr: Optional[int] = None, progress: Optional[Callable[[int, int], None]] = None,
-               count: bool = False):
-        """Camera::render.  Returns (image (H, W, 3) float32 or None for device output, stats dict)."""
+               count: bool = False, packed: bool = False):
+        """Camera::render.  Returns (image (H, W, 3) float32 or None for device output, stats dict).
+        packed=True: the output buffer holds only this rank's rows, packed (NRRT_RENDER_OUT_PACKED)."""
         opts = A.RenderOpts(seed=seed, mode=mode, rank=rank, world=world, rows_per_block=rows_per_block,
                             max_slots=max_slots, flags=(A.RENDER_OUT_DEVICE if out_device_ptr is not None else 0) |
-                            (A.RENDER_COUNT if count else 0))
+                            (A.RENDER_COUNT if count else 0) | (A.RENDER_OUT_PACKED if packed else 0))
         st = A.RenderStats()
         cb = A.PROGRESS_FN(lambda done, total, user: progress(done, total)) if progress else None
         if out_device_ptr is not None:
@@ -264,12 +267,12 @@ class Context:
         else:
             if out is None:
                 out = np.zeros((cam.height, cam.width, 3), dtype=np.float32)
-            assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == cam.height * cam.width * 3
+            assert out.dtype == np.float32 and out.flags.c_contiguous and (packed or out.size == cam.height * cam.width * 3)
             ptr = C.c_void_p(out.ctypes.data)
         self._check(lib().nrrt_render(self._h, C.byref(cam), C.byref(opts), ptr, C.cast(cb, C.c_void_p) if cb else None,
                                       None, C.byref(st)))
         stats = {k: getattr(st, k) for k in ("paths", "segments", "launches", "device_ms", "extend_ms",
-                                             "extend_launches", "pixels", "node_visits", "box_exact",
+                                             "extend_launches", "pixels", "mode", "node_visits", "box_exact",
                                              "prim_tests", "inst_entries", "inst_misses")}
         return (None if out_device_ptr is not None else out), stats
 

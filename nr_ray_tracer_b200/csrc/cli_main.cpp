@@ -5,7 +5,7 @@
 //   ->  build  ->  scene.render()  ->  gamma_correction(gamma)  ->  to_rgb8  ->  encode by extension
 // Flags and NR_RT_CAMERA_* environment fallbacks follow ray-tracer/src/cli.rs:113-270 (field of view and defocus
 // angle in degrees; image size needs exactly two of width / height / aspect ratio; default output out.png,
-// default gamma 0.5).  Additions: --seed, --mode fused|wavefront|megakernel, --device N.
+// default gamma 0.5).  Additions: --seed, --mode auto|pool|fused|wavefront|megakernel, --device N.
 // Encoders available without external libraries: .png (stored/uncompressed deflate) and .ppm.
 #include <cerrno>
 #include <chrono>
@@ -122,7 +122,7 @@ static void usage() {
         "      --background-color x,y,z  --look-at x,y,z  --look-from x,y,z  --view-up x,y,z\n"
         "      --field-of-view <DEG>  --defocus-angle <DEG>  --focus-distance <D>\n"
         "      --samples-per-pixel <N>  --ray-max-bounces <N>\n"
-        "      --seed <N>  --mode fused|wavefront|megakernel  --device <N>\n"
+        "      --seed <N>  --mode auto|pool|fused|wavefront|megakernel  --device <N>\n"
         "      --bvh reference|sah   reference = the reference's BVH (default), sah = surface-area-heuristic inner nodes\n"
         "  -v, --verbose                  print timing\n"
         "Every camera option falls back to NR_RT_CAMERA_<NAME> (e.g. NR_RT_CAMERA_SAMPLES_PER_PIXEL).");
@@ -164,7 +164,7 @@ int main(int argc, char** argv) {
     }
     if (std::strcmp(argv[1], "create") == 0) return run_create(argc, argv);
     if (std::strcmp(argv[1], "render") != 0) die(std::string("unknown command '") + argv[1] + "' (commands: render, create)");
-    std::string scene_path, output = "out.png", mode = "fused", bvh = "reference";
+    std::string scene_path, output = "out.png", mode = "auto", bvh = "reference";
     bool force = false, verbose = false;
     float gamma = 0.5f;  // constants.rs:1
     uint64_t seed = 0;
@@ -280,7 +280,15 @@ int main(int argc, char** argv) {
     std::memset(&opts, 0, sizeof opts);
     opts.seed = seed;
     opts.world = 1;
-    opts.mode = mode == "megakernel" ? NRRT_MODE_MEGAKERNEL : (mode == "wavefront" ? NRRT_MODE_WAVEFRONT : NRRT_MODE_FUSED);
+    if (mode == "megakernel") opts.mode = NRRT_MODE_MEGAKERNEL;
+    else if (mode == "wavefront") opts.mode = NRRT_MODE_WAVEFRONT;
+    else if (mode == "fused") opts.mode = NRRT_MODE_FUSED;
+    else if (mode == "pool") opts.mode = NRRT_MODE_POOL;
+    else if (mode == "auto") opts.mode = NRRT_MODE_AUTO;
+    else {
+        std::fprintf(stderr, "error: unknown --mode '%s'\n", mode.c_str());
+        return 2;
+    }
     nrrt_render_stats st;
     auto t0 = std::chrono::steady_clock::now();
     // the reference draws a per-pixel progress bar (render.rs:48-59); with -v a percentage goes to stderr

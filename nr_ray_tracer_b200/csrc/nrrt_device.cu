@@ -101,7 +101,8 @@ __device__ __forceinline__ uint32_t decode_item(const nrrt_camera& cam, const Re
     return first;
 }
 
-template <bool VISIT_ALL, bool COUNT>
+// COMPACT: the closest-hit query alone — 16 bytes out per ray, no HitRecord (traversal microbenchmark)
+template <bool VISIT_ALL, bool COUNT, bool COMPACT = false>
 __global__ void __launch_bounds__(NRRT_BLOCK)
 k_trace_rays(const __grid_constant__ DevScene S, const double* __restrict__ rays, uint64_t n, double tmin, double tmax,
              double time, nrrt_hit* __restrict__ out, unsigned long long* __restrict__ counters) {
@@ -114,6 +115,12 @@ k_trace_rays(const __grid_constant__ DevScene S, const double* __restrict__ rays
     TraceCounters tc{0, 0, 0, 0, 0};
     trace_closest<VISIT_ALL, COUNT>(S, o, d, time, tmin, tmax, s_stack + threadIdx.x, NRRT_BLOCK, h, &tc, valid);
     if (!valid) return;
+    if (COMPACT) {
+        nrrt_hit_compact c;
+        c.t = h.t, c.prim = h.prim, c.depth_inst0 = h.depth | (h.inst.a << 3);
+        reinterpret_cast<nrrt_hit_compact*>(out)[i] = c;
+        return;
+    }
     nrrt_hit r;
     r.t = h.t;
     r.prim = h.prim;
@@ -268,7 +275,7 @@ k_render_mega(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
 // per-pixel sample accumulation: add the chunk partials in chunk order, divide by spp, cast to f32
 // (camera.rs:329-337)
 __global__ void k_resolve(const __grid_constant__ nrrt_camera cam, const __grid_constant__ RenderParams P,
-                          const double* __restrict__ partials, float* __restrict__ out) {
+                          const double* __restrict__ partials, float* __restrict__ out, bool packed) {
     uint32_t po = blockIdx.x * blockDim.x + threadIdx.x;
     if (po >= P.n_owned_pixels) return;
     d3 s = mk3(0.0, 0.0, 0.0);
@@ -279,7 +286,7 @@ __global__ void k_resolve(const __grid_constant__ nrrt_camera cam, const __grid_
     d3 col = div3(s, (double)cam.samples_per_pixel);
     uint32_t x, y;
     owned_pixel(cam, P, po, x, y);
-    size_t ob = ((size_t)y * cam.width + x) * 3;
+    size_t ob = (packed ? (size_t)po : (size_t)y * cam.width + x) * 3;  // owned pixels are numbered in ascending row order
     out[ob] = (float)col.x, out[ob + 1] = (float)col.y, out[ob + 2] = (float)col.z;
 }
 
@@ -910,6 +917,7 @@ int nrrt_set_trace_time(nrrt_ctx* ctx, double time) {
 
 static uint32_t pick_features(uint32_t need);
 #define NRRT_BINARY_MAX_NODES 64u  // scenes with fewer inner nodes are also uploaded in binary form (fused kernel)
+#define NRRT_POOL_MIN_NODES 1024u  // NRRT_MODE_AUTO: four-slot nodes from which the pooled kernel is the product path
 
 // Stack entries a traversal of the binary nodes can need, or a value above any cap when the arrays are unusable
 // (a reference out of range, children not after their parents).  Same sweep as for the four-slot nodes.
@@ -1390,10 +1398,11 @@ int nrrt_trace_rays(nrrt_ctx* ctx, const double* rays, uint64_t n, double tmin, 
     if (!rays || !out) return NRRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     const bool dev_buf = (flags & NRRT_TRACE_DEVICE_BUFFERS) != 0;
+    const size_t hit_bytes = (flags & NRRT_TRACE_COMPACT) ? sizeof(nrrt_hit_compact) : sizeof(nrrt_hit);
     const double* d_rays = rays;
     nrrt_hit* d_out = out;
     if (!dev_buf) {
-        size_t rb = (size_t)n * 6 * sizeof(double), hb = (size_t)n * sizeof(nrrt_hit);
+        size_t rb = (size_t)n * 6 * sizeof(double), hb = (size_t)n * hit_bytes;
         int rc = ensure_scratch(ctx, rb + hb);
         if (rc != NRRT_OK) return rc;
         d_rays = (const double*)ctx->scratch;
@@ -1403,9 +1412,14 @@ int nrrt_trace_rays(nrrt_ctx* ctx, const double* rays, uint64_t n, double tmin, 
     CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     dim3 grid((unsigned)((n + NRRT_BLOCK - 1) / NRRT_BLOCK)), block(NRRT_BLOCK);
     size_t smem = (size_t)NRRT_BLOCK * NRRT_STACK_CAP * sizeof(uint32_t);
-    const bool count = stats != nullptr && (flags & NRRT_TRACE_COUNT) != 0;
+    const bool count = stats != nullptr && (flags & NRRT_TRACE_COUNT) != 0 && !(flags & NRRT_TRACE_COMPACT);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (flags & NRRT_TRACE_VISIT_ALL) {
+    if (flags & NRRT_TRACE_COMPACT) {
+        if (flags & NRRT_TRACE_VISIT_ALL)
+            k_trace_rays<true, false, true><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, ctx->trace_time, d_out, ctx->d_counters);
+        else
+            k_trace_rays<false, false, true><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, ctx->trace_time, d_out, ctx->d_counters);
+    } else if (flags & NRRT_TRACE_VISIT_ALL) {
         if (count)
             k_trace_rays<true, true><<<grid, block, smem, ctx->stream>>>(ctx->dev, d_rays, n, tmin, tmax, ctx->trace_time, d_out, ctx->d_counters);
         else
@@ -1418,7 +1432,7 @@ int nrrt_trace_rays(nrrt_ctx* ctx, const double* rays, uint64_t n, double tmin, 
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    if (!dev_buf) CK(cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(nrrt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!dev_buf) CK(cudaMemcpyAsync(out, d_out, (size_t)n * hit_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     unsigned long long hc[3] = {0, 0, 0};
     if (stats) CK(cudaMemcpyAsync(hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1499,7 +1513,19 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     }
 
     const bool out_dev = (o.flags & NRRT_RENDER_OUT_DEVICE) != 0;
+    const bool packed = (o.flags & NRRT_RENDER_OUT_PACKED) != 0;
     const bool counting = (o.flags & NRRT_RENDER_COUNT) != 0;
+    // NRRT_MODE_AUTO: the pooled kernel wins where rays walk many nodes (measured on B200: 6319-node teapot 2045 vs
+    // 1391 Mrays/s, Cornell box + teapot 1894 vs 1480) and loses where shading dominates (487-node sphere field 4209 vs
+    // 4557, Cornell box 3735 vs 6161), so the split is by tree size
+    if (o.mode == NRRT_MODE_AUTO) {
+        o.mode = ctx->dev.n_nodes >= NRRT_POOL_MIN_NODES ? NRRT_MODE_POOL : NRRT_MODE_FUSED;
+        if (const char* e = std::getenv("NRRT_AUTO_MODE")) o.mode = (uint32_t)std::atoi(e);  // developer override
+    }
+    if (o.mode > NRRT_MODE_POOL) {
+        ctx->err = "nrrt_render: unknown mode";
+        return NRRT_ERR_INVALID;
+    }
     // (instance chains are packed as 16-bit indices in the pooled kernel's slot state: larger scenes use the fused kernel)
     const bool pooled = o.mode == NRRT_MODE_POOL && !counting && ctx->dev.n_instances <= 65536u;
     if (o.mode == NRRT_MODE_POOL && !counting && !pooled) o.mode = NRRT_MODE_FUSED;
@@ -1677,7 +1703,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         if (!timing.empty()) extend_ms = sampled / (double)timing.size() * (double)extend_launches;
     }
     if (P.n_owned_pixels) {
-        k_resolve<<<(P.n_owned_pixels + 255) / 256, 256, 0, ctx->stream>>>(c, P, d_part, d_fb);
+        k_resolve<<<(P.n_owned_pixels + 255) / 256, 256, 0, ctx->stream>>>(c, P, d_part, d_fb, packed);
         CK(cudaGetLastError());
         ++launches;
     }
@@ -1701,17 +1727,30 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
             std::this_thread::sleep_for(std::chrono::milliseconds(20));
         }
     }
-    if (!out_dev) {
+    if (!out_dev && packed) {
+        if (P.n_owned_pixels)
+            CK(cudaMemcpyAsync(out_rgb, d_fb, (size_t)P.n_owned_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (!out_dev) {
         // copy only the owned rows back into the caller's full-size buffer
         const uint32_t R = o.rows_per_block;
-        for (uint32_t b = o.rank; (uint64_t)b * R < H; b += o.world) {
-            size_t y0 = (size_t)b * R, rows = std::min<size_t>(R, H - y0);
-            size_t offb = y0 * W * 3 * sizeof(float), bytes = rows * W * 3 * sizeof(float);
-            if (o.world == 1) {  // one contiguous copy
-                offb = 0, bytes = fb_bytes;
+        const size_t row_bytes = (size_t)W * 3 * sizeof(float);
+        if (o.world == 1) {  // one contiguous copy
+            CK(cudaMemcpyAsync(out_rgb, d_fb, fb_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            // the owned row-blocks sit at a fixed pitch: one strided copy for the full blocks, one for a cut-off last one
+            size_t full_blocks = 0, tail_y0 = 0, tail_rows = 0;
+            for (uint32_t b = o.rank; (uint64_t)b * R < H; b += o.world) {
+                const size_t y0 = (size_t)b * R, rows = std::min<size_t>(R, H - y0);
+                if (rows == R) ++full_blocks;
+                else tail_y0 = y0, tail_rows = rows;
             }
-            CK(cudaMemcpyAsync((char*)out_rgb + offb, (char*)d_fb + offb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-            if (o.world == 1) break;
+            const size_t off0 = (size_t)o.rank * R * row_bytes, pitch = (size_t)o.world * R * row_bytes;
+            if (full_blocks)
+                CK(cudaMemcpy2DAsync((char*)out_rgb + off0, pitch, (char*)d_fb + off0, pitch, R * row_bytes, full_blocks,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+            if (tail_rows)
+                CK(cudaMemcpyAsync((char*)out_rgb + tail_y0 * row_bytes, (char*)d_fb + tail_y0 * row_bytes, tail_rows * row_bytes,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
         }
     }
     unsigned long long hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1728,7 +1767,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         stats->extend_ms = wavefront ? extend_ms : ms;
         stats->extend_launches = wavefront ? extend_launches : (launches ? 1 : 0);
         stats->pixels = P.n_owned_pixels;
-        stats->_pad = 0;
+        stats->mode = counting ? (uint32_t)NRRT_MODE_MEGAKERNEL : o.mode;
         stats->node_visits = hc[2];
         stats->box_exact = hc[3];
         stats->prim_tests = hc[4];
@@ -1797,6 +1836,7 @@ size_t nrrt_abi_sizeof(int which) {
         case 15: return sizeof(nrrt_render_stats);
         case 16: return sizeof(nrrt_camera_file);
         case 17: return sizeof(nrrt_wnode);
+        case 18: return sizeof(nrrt_hit_compact);
         default: return 0;
     }
 }

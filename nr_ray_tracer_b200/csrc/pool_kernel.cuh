@@ -22,8 +22,10 @@
 #define NRRT_POOL_WARPS 4  // warps per block
 #endif
 #ifndef NRRT_POOL_NODE_KEEP_NUM
-#define NRRT_POOL_NODE_KEEP_NUM 3  // the NODE stage goes on while >= KEEP_NUM/KEEP_DEN of the lanes it started with still
-#define NRRT_POOL_NODE_KEEP_DEN 4  // hold an inner node; below that the warp re-schedules (refills the lanes)
+#define NRRT_POOL_NODE_KEEP_NUM 1  // the NODE stage goes on while >= KEEP_NUM/KEEP_DEN of the lanes it started with still
+#define NRRT_POOL_NODE_KEEP_DEN 2  // hold an inner node; below that the warp re-schedules (refills the lanes).
+                                   // Measured on B200 (teapot / C5 / Cornell, Mrays/s): 7/8 1993 / 1840 / 3682, 3/4 2031 / 1881 /
+                                   // 3720, 1/2 2091 / 1949 / 3786.  Slots per warp: 48 1665, 56 1946, 64 2031, 80 1860.
 #endif
 #define NRRT_POOL_TRIVIAL_MAX 4     // camera rays that miss the scene's root box, absorbed per SHADE visit
 

@@ -60,6 +60,41 @@ def _worker(rank, world, port, H, W, R, out_path):
         dist.destroy_process_group()
 
 
+def _worker_packed(rank, world, port, H, W, out_path):
+    """The production path: rows rendered PACKED into FramebufferGather.packed (NRRT_RENDER_OUT_PACKED layout: the
+    rank's rows in ascending order), single-row interleave, one gather, one index_select on rank 0."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        R = D.rows_per_block_for(world)
+        assert R == 1
+        G = D.FramebufferGather(H, W, rank, world, R, torch.device("cpu"))
+        for rep in range(2):  # buffers are reused across calls
+            rows = D.owned_rows(H, rank, world, R)
+            assert G.n_rows == len(rows)
+            for k, y in enumerate(rows):  # a recognisable pattern: value = row * 1000 + column + repetition
+                G.packed[k] = torch.arange(W, dtype=torch.float32)[:, None] + float(y) * 1000.0 + rep
+            full = G.gather()
+            if rank == 0:
+                want = torch.arange(H, dtype=torch.float32)[:, None, None] * 1000.0 + \
+                    torch.arange(W, dtype=torch.float32)[None, :, None] + torch.zeros(3) + rep
+                assert torch.equal(full, want)
+            else:
+                assert full is None
+        if rank == 0:
+            np.save(out_path, full.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,H", [(2, 9), (3, 10)])
+def test_gloo_packed_gather_with_single_row_interleave(tmp_path, world, H):
+    out_path = str(tmp_path / "full.npy")
+    mp.spawn(_worker_packed, args=(world, _free_port(), H, 5, out_path), nprocs=world, join=True)
+    assert np.load(out_path).shape == (H, 5, 3)
+
+
 @pytest.mark.parametrize("world,H,R", [(2, 20, 8), (3, 13, 2)])
 def test_gloo_gather_reassembles_the_image(tmp_path, world, H, R):
     W = 16

@@ -248,6 +248,35 @@ def test_tile_partition_is_bit_identical_to_single_gpu(gpu_ctx):
     del hs
 
 
+def test_packed_output_is_the_owned_rows_in_order(gpu_ctx):
+    """NRRT_RENDER_OUT_PACKED (what a multi-GPU gather sends): a rank's rows, ascending, nothing else — for host and
+    device output buffers, block heights 1 and 8, a height that is not a multiple of the block."""
+    import torch
+    g = load("cornell-box-scene.json", width=64, height=37, samples_per_pixel=2)
+    hs = _scene(gpu_ctx, g)
+    cam = api.camera_build(g.camera.to_builder_config())
+    full, _ = gpu_ctx.render(cam, seed=5)
+    from nr_ray_tracer_b200 import distributed as D
+    for world, R in ((1, 8), (2, 1), (3, 8), (8, 1)):
+        for rank in range(world):
+            rows = D.owned_rows(37, rank, world, R)
+            out = np.full((max(len(rows), 1), 64, 3), np.nan, dtype=np.float32)
+            _, st = gpu_ctx.render(cam, out=out, seed=5, rank=rank, world=world, rows_per_block=R, packed=True)
+            assert st["pixels"] == len(rows) * 64
+            assert np.array_equal(out[:len(rows)], full[rows]), (world, R, rank)
+            dev = torch.full((max(len(rows), 1), 64, 3), float("nan"), device="cuda")
+            gpu_ctx.render(cam, seed=5, rank=rank, world=world, rows_per_block=R, packed=True, out_device_ptr=dev.data_ptr())
+            torch.cuda.synchronize()
+            assert np.array_equal(dev.cpu().numpy()[:len(rows)], full[rows])
+            # un-packed host output with a strided copy: only the owned rows are touched
+            asm = np.full((37, 64, 3), np.nan, dtype=np.float32)
+            gpu_ctx.render(cam, out=asm, seed=5, rank=rank, world=world, rows_per_block=R)
+            assert np.array_equal(asm[rows], full[rows])
+            other = np.setdiff1d(np.arange(37), rows)
+            assert np.isnan(asm[other]).all()
+    del hs
+
+
 def test_full_size_properties_1080p(gpu_ctx):
     """BASELINE size (1920x1080) at low spp: determinism, kernel-design invariance, seed sensitivity,
     non-negativity and the exact path count — properties that do not need the (slow) oracle."""

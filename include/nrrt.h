@@ -452,6 +452,22 @@ typedef void (*nrrt_progress_fn)(uint64_t pixels_done, uint64_t pixels_total, vo
 int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* camera, const nrrt_render_opts* opts,
                 float* out_rgb, nrrt_progress_fn progress, void* user, nrrt_render_stats* stats);
 
+/* Camera::render over several GPUs of one box from ONE process (what `nr-ray-tracer render --gpus N` calls; the
+ * one-process-per-GPU form with torch.distributed / NCCL is nr_ray_tracer_b200/distributed.py).  One host thread and
+ * one context per device: every device uploads the scene, renders the rows r with r % n_devices == its index end to
+ * end (same Philox streams, so the image is bit-identical to a single-GPU render) and the rows are brought together
+ * inside the library:
+ *   - host out_rgb (default): each device copies its rows straight into the caller's image with one strided D2H
+ *     copy, all devices in parallel over their own PCIe links;
+ *   - NRRT_RENDER_OUT_DEVICE: out_rgb is memory of devices[0]; the other devices render packed rows, push them to
+ *     devices[0] with peer-to-peer copies over NVLink and one kernel there places them.
+ * opts->rank / world / rows_per_block are ignored (set per device).  stats (may be NULL): paths, segments, launches
+ * and pixels summed over the devices, device_ms = the slowest device.  progress (may be NULL) is called under a lock
+ * with the pixels finished on all devices.  err (may be NULL) receives the message of the first failing device. */
+int nrrt_render_multi(const int* devices, int n_devices, const nrrt_scene_desc* scene, const nrrt_camera* camera,
+                      const nrrt_render_opts* opts, float* out_rgb, nrrt_progress_fn progress, void* user,
+                      nrrt_render_stats* stats, char* err, size_t err_len);
+
 /* Output stage (§8(f) N2): gamma_correction (image.rs:53-57: p.powf(gamma) per channel, f32) followed by
  * DynamicImage::to_rgb8 (render.rs:85-86: clamp to [0,1], x255, round) on the GPU, so only W*H*3 bytes cross PCIe.
  * `rgb` is W*H*3 f32 (device pointer if NRRT_RENDER_OUT_DEVICE is set in flags, else host); `out_rgb8` is a

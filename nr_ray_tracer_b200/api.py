@@ -69,6 +69,9 @@ def lib() -> C.CDLL:
         L.nrrt_render.argtypes = [C.c_void_p, C.POINTER(A.Camera), C.POINTER(A.RenderOpts), C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.POINTER(A.RenderStats)]
         L.nrrt_encode_rgb8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32, C.c_void_p]
+        L.nrrt_render_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(A.SceneDesc), C.POINTER(A.Camera),
+                                        C.POINTER(A.RenderOpts), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.POINTER(A.RenderStats), C.c_char_p, C.c_size_t]
         L.nrrt_abi_sizeof.restype = C.c_size_t
         L.nrrt_abi_sizeof.argtypes = [C.c_int]
         _lib = L
@@ -290,6 +293,29 @@ class Context:
         out = np.zeros((h, w, 3), dtype=np.uint8)
         self._check(lib().nrrt_encode_rgb8(self._h, ptr, w, h, gamma, flags, C.c_void_p(out.ctypes.data)))
         return out
+
+
+def render_multi(devices, host_scene: "HostScene", cam: A.Camera, out: Optional[np.ndarray] = None, seed: int = 0,
+                 mode: int = A.MODE_AUTO, out_device_ptr: Optional[int] = None):
+    """Camera::render over several GPUs of one box from this one process (nrrt_render_multi): rows interleaved over
+    `devices`, brought together inside the library (host image: parallel D2H copies; device image on devices[0]:
+    peer-to-peer copies + one placement kernel).  Returns (image or None, stats summed over the devices)."""
+    devs = (C.c_int * len(devices))(*devices)
+    opts = A.RenderOpts(seed=seed, mode=mode, flags=A.RENDER_OUT_DEVICE if out_device_ptr is not None else 0)
+    st = A.RenderStats()
+    if out_device_ptr is not None:
+        ptr = C.c_void_p(out_device_ptr)
+    else:
+        if out is None:
+            out = np.zeros((cam.height, cam.width, 3), dtype=np.float32)
+        ptr = C.c_void_p(out.ctypes.data)
+    err = C.create_string_buffer(512)
+    rc = lib().nrrt_render_multi(devs, len(devices), C.byref(host_scene.desc), C.byref(cam), C.byref(opts), ptr, None, None,
+                                 C.byref(st), err, 512)
+    if rc != 0:
+        raise NrrtError(rc, err.value.decode())
+    stats = {k: getattr(st, k) for k in ("paths", "segments", "launches", "device_ms", "pixels", "mode")}
+    return (None if out_device_ptr is not None else out), stats
 
 
 class Scene:

@@ -5,7 +5,7 @@
 //   ->  build  ->  scene.render()  ->  gamma_correction(gamma)  ->  to_rgb8  ->  encode by extension
 // Flags and NR_RT_CAMERA_* environment fallbacks follow ray-tracer/src/cli.rs:113-270 (field of view and defocus
 // angle in degrees; image size needs exactly two of width / height / aspect ratio; default output out.png,
-// default gamma 0.5).  Additions: --seed, --mode auto|pool|fused|wavefront|megakernel, --device N.
+// default gamma 0.5).  Additions: --seed, --mode auto|pool|fused|wavefront|megakernel, --device N, --gpus N.
 // Encoders available without external libraries: .png (stored/uncompressed deflate) and .ppm.
 #include <cerrno>
 #include <chrono>
@@ -111,6 +111,20 @@ static void write_ppm(FILE* f, const uint8_t* rgb, uint32_t w, uint32_t h) {
     std::fwrite(rgb, 1, (size_t)w * h * 3, f);
 }
 
+// Unsigned decimal integer, whole string, no sign, <= max (clap rejects "-1", "1e3", "" and overflow alike).
+static bool parse_u64(const char* s, uint64_t max, uint64_t* out) {
+    if (!s || !*s) return false;
+    uint64_t x = 0;
+    for (const char* p = s; *p; ++p) {
+        if (*p < '0' || *p > '9') return false;
+        const uint64_t dgt = (uint64_t)(*p - '0');
+        if (x > (max - dgt) / 10) return false;
+        x = x * 10 + dgt;
+    }
+    *out = x;
+    return true;
+}
+
 static void usage() {
     std::puts(
         "Usage: nr-ray-tracer render [OPTIONS] <SCENE>\n"
@@ -123,6 +137,8 @@ static void usage() {
         "      --field-of-view <DEG>  --defocus-angle <DEG>  --focus-distance <D>\n"
         "      --samples-per-pixel <N>  --ray-max-bounces <N>\n"
         "      --seed <N>  --mode auto|pool|fused|wavefront|megakernel  --device <N>\n"
+        "      --gpus <N>                 render on GPUs device .. device+N-1 of this box (rows interleaved across them,\n"
+        "                                 same image bit for bit; env NR_RT_GPUS)\n"
         "      --bvh reference|sah   reference = the reference's BVH (default), sah = surface-area-heuristic inner nodes\n"
         "  -v, --verbose                  print timing\n"
         "Every camera option falls back to NR_RT_CAMERA_<NAME> (e.g. NR_RT_CAMERA_SAMPLES_PER_PIXEL).");
@@ -168,20 +184,26 @@ int main(int argc, char** argv) {
     bool force = false, verbose = false;
     float gamma = 0.5f;  // constants.rs:1
     uint64_t seed = 0;
-    int device = 0;
+    int device = 0, gpus = 1;
+    if (const char* e = std::getenv("NR_RT_GPUS")) {
+        uint64_t x = 0;
+        if (!parse_u64(e, 64, &x) || x == 0) die("invalid value '" + std::string(e) + "' in NR_RT_GPUS");
+        gpus = (int)x;
+    }
     nrrt_camera_file cli;
     std::memset(&cli, 0, sizeof cli);
 
     auto set_camera = [&](const std::string& name, const char* val) -> bool {
         char* e = nullptr;
-        auto u = [&](uint32_t& dst, uint32_t bit) {
-            unsigned long long x = std::strtoull(val, &e, 10);
-            if (!e || *e) return false;
+        auto u = [&](uint32_t& dst, uint32_t bit) {  // clap's u32 parser: digits only, no sign, must fit
+            uint64_t x = 0;
+            if (!parse_u64(val, 0xFFFFFFFFull, &x)) return false;
             dst = (uint32_t)x;
             cli.present |= bit;
             return true;
         };
         auto d = [&](double& dst, uint32_t bit) {
+            if (!*val) return false;
             dst = std::strtod(val, &e);
             if (!e || *e) return false;
             cli.present |= bit;
@@ -234,18 +256,37 @@ int main(int argc, char** argv) {
         if (a == "-f" || a == "--force-overwrite") force = true;
         else if (a == "-v" || a == "--verbose") verbose = true;
         else if (a == "-o" || a == "--output") output = need();
-        else if (a == "--gamma-value") gamma = (float)std::atof(need());
-        else if (a == "--seed") seed = std::strtoull(need(), nullptr, 10);
-        else if (a == "--mode") mode = need();
+        else if (a == "--gamma-value") {
+            const char* v = need();
+            char* e = nullptr;
+            gamma = std::strtof(v, &e);
+            if (!*v || !e || *e) die("invalid value '" + std::string(v) + "' for --gamma-value");
+        } else if (a == "--seed") {
+            const char* v = need();
+            if (!parse_u64(v, ~0ull, &seed)) die("invalid value '" + std::string(v) + "' for --seed");
+        } else if (a == "--mode") mode = need();
         else if (a == "--bvh") bvh = need();
-        else if (a == "--device") device = std::atoi(need());
+        else if (a == "--device") {
+            const char* v = need();
+            uint64_t x = 0;
+            if (!parse_u64(v, 1023, &x)) die("invalid value '" + std::string(v) + "' for --device");
+            device = (int)x;
+        } else if (a == "--gpus") {
+            const char* v = need();
+            uint64_t x = 0;
+            if (!parse_u64(v, 64, &x) || x == 0) die("invalid value '" + std::string(v) + "' for --gpus");
+            gpus = (int)x;
+        }
         else if (a == "-W") { if (!set_camera("width", need())) die("invalid width"); }
         else if (a == "-H") { if (!set_camera("height", need())) die("invalid height"); }
         else if (a.rfind("--", 0) == 0) {
             std::string name = a.substr(2);
+            bool known = false;
+            for (const char* n : cam_names) known = known || name == n;
+            if (!known) die("unknown option '" + a + "'");  // (without consuming the next argument)
             const char* v = need();
-            if (!set_camera(name, v)) die("invalid option or value: " + a + " " + v);
-        } else if (scene_path.empty()) scene_path = a;
+            if (!set_camera(name, v)) die("invalid value '" + std::string(v) + "' for " + a);
+        } else if (a.size() > 1 && a[0] == '-') die("unknown option '" + a + "'"); else if (scene_path.empty()) scene_path = a;
         else die("unexpected argument '" + a + "'");
     }
     if (scene_path.empty()) die("missing <SCENE>");
@@ -271,9 +312,9 @@ int main(int argc, char** argv) {
     if (bvh != "reference" && bvh != "sah") die("--bvh must be reference or sah");
     nrrt_host_scene* hs = nrrt_host_build_ex(nrrt_loaded_graph(ls), bvh == "sah" ? NRRT_BUILD_SAH : NRRT_BUILD_REFERENCE);
     if (!hs) die(nrrt_host_last_error());
-    nrrt_ctx* ctx = nullptr;
+    nrrt_ctx* ctx = nullptr;  // device `device`: single-GPU render, and the output stage in every case
     if (nrrt_create(device, &ctx) != NRRT_OK) die(nrrt_last_error(nullptr));
-    if (nrrt_scene_upload(ctx, nrrt_host_scene_desc(hs)) != NRRT_OK) die(nrrt_last_error(ctx));
+    if (gpus == 1 && nrrt_scene_upload(ctx, nrrt_host_scene_desc(hs)) != NRRT_OK) die(nrrt_last_error(ctx));
 
     std::vector<float> image((size_t)cam.width * cam.height * 3);
     nrrt_render_opts opts;
@@ -296,7 +337,14 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "\rrendering: %3u%%", total ? (unsigned)(done * 100 / total) : 100u);
         if (done >= total) std::fputc('\n', stderr);
     };
-    if (nrrt_render(ctx, &cam, &opts, image.data(), verbose ? on_progress : nullptr, nullptr, &st) != NRRT_OK)
+    if (gpus > 1) {  // one host thread + context per device inside the library, rows land in `image` directly
+        std::vector<int> devs;
+        for (int k = 0; k < gpus; ++k) devs.push_back(device + k);
+        char msg[512] = "";
+        if (nrrt_render_multi(devs.data(), gpus, nrrt_host_scene_desc(hs), &cam, &opts, image.data(),
+                              verbose ? on_progress : nullptr, nullptr, &st, msg, sizeof msg) != NRRT_OK)
+            die(msg);
+    } else if (nrrt_render(ctx, &cam, &opts, image.data(), verbose ? on_progress : nullptr, nullptr, &st) != NRRT_OK)
         die(nrrt_last_error(ctx));
     auto t1 = std::chrono::steady_clock::now();
     std::vector<uint8_t> rgb8(image.size());

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <chrono>
@@ -754,7 +755,7 @@ k_wf_shade(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_came
 }
 
 // =========================================================================== host side of the ABI
-static std::string g_create_error;
+static thread_local std::string g_create_error;  // per thread: nrrt_create may run on several threads (nrrt_render_multi)
 
 struct nrrt_ctx {
     int device = 0;
@@ -780,6 +781,8 @@ struct nrrt_ctx {
     double trace_time = 0.0;           // Ray::time of nrrt_trace_rays queries
     bool speculate = false;            // fused kernel: speculative traversal (deep trees only)
     cudaStream_t side = nullptr;       // progress polling while a single-launch render runs (created on first use)
+    void* enc_buf = nullptr;           // output-stage scratch (nrrt_encode_rgb8), grown on demand
+    size_t enc_bytes = 0;
 };
 
 #define CK(call)                                                                                   \
@@ -892,6 +895,7 @@ void nrrt_destroy(nrrt_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->enc_buf) cudaFree(ctx->enc_buf);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_count) cudaFreeHost(ctx->h_count);
     if (ctx->side) cudaStreamDestroy(ctx->side);
@@ -1212,7 +1216,7 @@ int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
     UP(image_tex, objs.data(), objs.size());
     UP(image_size, sizes.data(), sizes.size());
 #undef UP
-    D.n_nodes = sc->n_nodes, D.n_spheres = sc->n_spheres, D.n_planes = sc->n_planes;
+    D.n_nodes = sc->n_nodes, D.n_wnodes = sc->n_wnodes, D.n_spheres = sc->n_spheres, D.n_planes = sc->n_planes;
     D.n_instances = sc->n_instances, D.n_materials = sc->n_materials, D.n_textures = sc->n_textures;
     CK(cudaStreamSynchronize(ctx->stream));  // host staging vectors die at return
     {
@@ -1301,6 +1305,7 @@ static cudaError_t launch_fused(nrrt_ctx* ctx, unsigned blocks, const nrrt_camer
 #define NRRT_POOL_NS 64  // path slots per warp
 #endif
 extern "C++" {
+#define NRRT_POOL_STATIC_SMEM 1024  // the opt-in limit covers static + dynamic shared memory; the kernel has 16 B static
 struct PoolPlan {
     unsigned warps_per_block = 0, blocks_per_sm = 0;
     size_t smem = 0, cold_bytes_per_slot = 0;
@@ -1320,8 +1325,11 @@ static PoolPlan pool_plan_f(const nrrt_ctx* ctx) {
     for (unsigned wpb = NRRT_POOL_WARPS; wpb >= 1; --wpb) {
         if (force && wpb != force) continue;
         const size_t smem = wpb * bpw;
-        if (smem > ctx->smem_per_block) continue;
-        if (cudaFuncSetAttribute(k_render_pool<F, NRRT_POOL_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (smem + NRRT_POOL_STATIC_SMEM > ctx->smem_per_block) continue;
+        // (the attribute is a per-function limit shared by every host thread: always the device maximum, never a
+        // per-launch value another thread's launch could find lowered — nrrt_render_multi renders from several threads)
+        if (cudaFuncSetAttribute(k_render_pool<F, NRRT_POOL_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)ctx->smem_per_block - NRRT_POOL_STATIC_SMEM) != cudaSuccess)
             continue;
         int blocks = 0;  // resident blocks per SM: shared memory AND registers
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_render_pool<F, NRRT_POOL_NS>, (int)wpb * 32, smem) != cudaSuccess)
@@ -1355,7 +1363,8 @@ static cudaError_t launch_pool(nrrt_ctx* ctx, const PoolPlan& pl, const nrrt_cam
     const uint32_t cold_slots = blocks * pl.warps_per_block * NRRT_POOL_NS;
     cudaError_t e = cudaSuccess;
 #define NRRT_POOL_LAUNCH(FEAT)                                                                                            \
-    e = cudaFuncSetAttribute(k_render_pool<FEAT, NRRT_POOL_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem); \
+    e = cudaFuncSetAttribute(k_render_pool<FEAT, NRRT_POOL_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                             (int)ctx->smem_per_block - NRRT_POOL_STATIC_SMEM);                                           \
     if (e == cudaSuccess)                                                                                                 \
         k_render_pool<FEAT, NRRT_POOL_NS><<<blocks, pl.warps_per_block * 32, pl.smem, ctx->stream>>>(                     \
             ctx->dev, c, P, partials, ctx->d_counters, pl.cap, cold, cold_slots);
@@ -1777,6 +1786,137 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     return NRRT_OK;
 }
 
+// rows of one rank, packed -> their places in the full image (device-output form of nrrt_render_multi)
+__global__ void k_place_rows(const float* __restrict__ packed, float* __restrict__ full, uint32_t row_floats, uint32_t n_rows,
+                             uint32_t rank, uint32_t world) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n_rows * row_floats) return;
+    const uint32_t k = (uint32_t)(i / row_floats), c = (uint32_t)(i - (size_t)k * row_floats);
+    full[((size_t)k * world + rank) * row_floats + c] = packed[i];
+}
+
+int nrrt_render_multi(const int* devices, int n_devices, const nrrt_scene_desc* scene, const nrrt_camera* camera,
+                      const nrrt_render_opts* opts_in, float* out_rgb, nrrt_progress_fn progress, void* user,
+                      nrrt_render_stats* stats, char* err, size_t err_len) {
+    auto fail = [&](const std::string& m, int code) {
+        if (err && err_len) std::snprintf(err, err_len, "%s", m.c_str());
+        return code;
+    };
+    if (!devices || n_devices <= 0 || !scene || !camera || !out_rgb) return fail("nrrt_render_multi: bad arguments", NRRT_ERR_INVALID);
+    nrrt_render_opts base;
+    std::memset(&base, 0, sizeof base);
+    if (opts_in) base = *opts_in;
+    const bool out_dev = (base.flags & NRRT_RENDER_OUT_DEVICE) != 0;
+    if (base.flags & NRRT_RENDER_OUT_PACKED) return fail("nrrt_render_multi: NRRT_RENDER_OUT_PACKED makes no sense here", NRRT_ERR_INVALID);
+    const uint32_t world = (uint32_t)n_devices, W = camera->width, H = camera->height;
+    const size_t row_floats = (size_t)W * 3;
+    struct Rank {
+        nrrt_ctx* ctx = nullptr;
+        int rc = NRRT_OK;
+        std::string msg;
+        nrrt_render_stats st{};
+        float* d_packed = nullptr;  // device-output form: this rank's packed rows
+        uint32_t n_rows = 0;
+    };
+    std::vector<Rank> ranks(world);
+    std::mutex lock;
+    std::vector<uint64_t> done(world, 0), total(world, 0);
+    struct ProgressCtx {
+        std::mutex* lock;
+        std::vector<uint64_t>*done, *total;
+        uint32_t rank;
+        nrrt_progress_fn fn;
+        void* user;
+    };
+    auto on_progress = [](uint64_t d, uint64_t t, void* u) {
+        ProgressCtx* p = (ProgressCtx*)u;
+        std::lock_guard<std::mutex> g(*p->lock);
+        (*p->done)[p->rank] = d, (*p->total)[p->rank] = t;
+        uint64_t ds = 0, ts = 0;
+        for (size_t i = 0; i < p->done->size(); ++i) ds += (*p->done)[i], ts += (*p->total)[i];
+        p->fn(ds, ts, p->user);
+    };
+    auto work = [&](uint32_t r) {
+        Rank& R = ranks[r];
+        if ((R.rc = nrrt_create(devices[r], &R.ctx)) != NRRT_OK) {
+            R.msg = nrrt_last_error(nullptr);
+            return;
+        }
+        if ((R.rc = nrrt_scene_upload(R.ctx, scene)) != NRRT_OK) {
+            R.msg = nrrt_last_error(R.ctx);
+            return;
+        }
+        nrrt_render_opts o = base;
+        o.rank = r, o.world = world, o.rows_per_block = world > 1 ? 1 : 0;
+        float* out = out_rgb;
+        R.n_rows = owned_rows(H, r, world, world > 1 ? 1 : 8);
+        if (out_dev && world > 1) {  // packed rows on this device, gathered on devices[0] below
+            if (cudaMalloc((void**)&R.d_packed, std::max<size_t>(1, (size_t)R.n_rows * row_floats * sizeof(float))) != cudaSuccess) {
+                R.rc = NRRT_ERR_CUDA, R.msg = "cudaMalloc (packed rows)";
+                return;
+            }
+            o.flags |= NRRT_RENDER_OUT_PACKED;
+            out = R.d_packed;
+        }
+        ProgressCtx pc{&lock, &done, &total, r, progress, user};
+        R.rc = nrrt_render(R.ctx, camera, &o, out, progress ? +on_progress : nullptr, &pc, &R.st);
+        if (R.rc != NRRT_OK) R.msg = nrrt_last_error(R.ctx);
+    };
+    std::vector<std::thread> threads;
+    for (uint32_t r = 1; r < world; ++r) threads.emplace_back(work, r);
+    work(0);
+    for (auto& t : threads) t.join();
+    int rc = NRRT_OK;
+    std::string msg;
+    for (uint32_t r = 0; r < world && rc == NRRT_OK; ++r)
+        if (ranks[r].rc != NRRT_OK) rc = ranks[r].rc, msg = "device " + std::to_string(devices[r]) + ": " + ranks[r].msg;
+    if (rc == NRRT_OK && out_dev && world > 1) {
+        // gather on devices[0]: peer copies of the packed rows over NVLink, then one placement kernel per rank
+        cudaError_t e = cudaSetDevice(devices[0]);
+        float* staging = nullptr;
+        size_t max_rows = 0;
+        for (auto& R : ranks) max_rows = std::max<size_t>(max_rows, R.n_rows);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&staging, std::max<size_t>(1, max_rows * row_floats * sizeof(float)));
+        for (uint32_t r = 0; r < world && e == cudaSuccess; ++r) {
+            const Rank& R = ranks[r];
+            if (!R.n_rows) continue;
+            const size_t bytes = (size_t)R.n_rows * row_floats * sizeof(float);
+            const float* src = R.d_packed;
+            if (r != 0) {
+                e = cudaMemcpyPeer(staging, devices[0], R.d_packed, devices[r], bytes);
+                src = staging;
+            }
+            if (e != cudaSuccess) break;
+            const size_t n = (size_t)R.n_rows * row_floats;
+            k_place_rows<<<(unsigned)((n + 255) / 256), 256>>>(src, out_rgb, (uint32_t)row_floats, R.n_rows, r, world);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        }
+        if (staging) cudaFree(staging);
+        if (e != cudaSuccess) rc = NRRT_ERR_CUDA, msg = std::string("gather on device 0: ") + cudaGetErrorString(e);
+    }
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        for (auto& R : ranks) {
+            stats->paths += R.st.paths, stats->segments += R.st.segments, stats->launches += R.st.launches;
+            stats->pixels += R.st.pixels;
+            stats->device_ms = std::max(stats->device_ms, R.st.device_ms);
+            stats->extend_ms = std::max(stats->extend_ms, R.st.extend_ms);
+            stats->extend_launches += R.st.extend_launches;
+            stats->mode = R.st.mode;
+        }
+    }
+    for (uint32_t r = 0; r < world; ++r) {
+        if (ranks[r].d_packed) {
+            cudaSetDevice(devices[r]);
+            cudaFree(ranks[r].d_packed);
+        }
+        nrrt_destroy(ranks[r].ctx);
+    }
+    if (rc != NRRT_OK) return fail(msg, rc);
+    return NRRT_OK;
+}
+
 int nrrt_encode_rgb8(nrrt_ctx* ctx, const float* rgb, uint32_t width, uint32_t height, float gamma, uint32_t flags,
                      uint8_t* out_rgb8) {
     if (!ctx) return NRRT_ERR_INVALID;
@@ -1787,31 +1927,28 @@ int nrrt_encode_rgb8(nrrt_ctx* ctx, const float* rgb, uint32_t width, uint32_t h
     CK(cudaSetDevice(ctx->device));
     const size_t n = (size_t)width * height * 3;
     const bool in_dev = (flags & NRRT_RENDER_OUT_DEVICE) != 0;
-    // the render scratch may hold a framebuffer the caller passed back in; carve above it
-    size_t need = ((n + 255) & ~(size_t)255) + (in_dev ? 0 : n * sizeof(float) + 256);
-    void* tmp = nullptr;
-    CK(cudaMalloc(&tmp, need));
-    uint8_t* d_out = (uint8_t*)tmp;
+    // own scratch, kept across calls (the render scratch may hold the very framebuffer being encoded)
+    const size_t need = ((n + 255) & ~(size_t)255) + (in_dev ? 0 : n * sizeof(float) + 256);
+    if (ctx->enc_bytes < need) {
+        if (ctx->enc_buf) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaFree(ctx->enc_buf));
+            ctx->enc_buf = nullptr, ctx->enc_bytes = 0;
+        }
+        CK(cudaMalloc(&ctx->enc_buf, need));
+        ctx->enc_bytes = need;
+    }
+    uint8_t* d_out = (uint8_t*)ctx->enc_buf;
     const float* d_in = rgb;
     if (!in_dev) {
-        float* staged = (float*)((char*)tmp + ((n + 255) & ~(size_t)255));
-        cudaError_t e = cudaMemcpyAsync(staged, rgb, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-        if (e != cudaSuccess) {
-            cudaFree(tmp);
-            ctx->err = std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e);
-            return NRRT_ERR_CUDA;
-        }
+        float* staged = (float*)((char*)ctx->enc_buf + ((n + 255) & ~(size_t)255));
+        CK(cudaMemcpyAsync(staged, rgb, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         d_in = staged;
     }
     k_encode_rgb8<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_in, n, gamma, d_out);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_rgb8, d_out, n, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(tmp);
-    if (e != cudaSuccess) {
-        ctx->err = std::string("nrrt_encode_rgb8: ") + cudaGetErrorString(e);
-        return NRRT_ERR_CUDA;
-    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_rgb8, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return NRRT_OK;
 }
 

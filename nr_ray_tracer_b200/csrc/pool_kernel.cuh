@@ -81,6 +81,7 @@ struct Pool {
     double* CD;       // cold doubles, already offset to this warp's first slot
     uint32_t* CW;     // cold words, likewise
     size_t cstride;   // pool slots in the launch
+    uint32_t cap;     // traversal stack entries per slot
     __device__ __forceinline__ double& d(int k, uint32_t s) const { return D[k * NS + s]; }
     __device__ __forceinline__ uint32_t& w(int k, uint32_t s) const { return W[k * NS + s]; }
     __device__ __forceinline__ double& cd(int k, uint32_t s) const { return CD[(size_t)k * cstride + s]; }
@@ -186,6 +187,7 @@ __device__ __forceinline__ void pool_node(const DevScene& S, const Pool<F, NS>& 
             const uint32_t n = wide_visit<false, false>(
                 S, r32, tmin32, tmax32, tcull, NRRT_REF_INDEX(cur), 0.001, NRRT_INF,
                 [&](d3& oo, d3& dd) { P.ld_ray(s, oo, dd); }, nullptr, nxt);
+            NRRT_CHECK(sp + (n ? n - 1 : 0) <= P.cap, "pool traversal stack overflow");
             if (n > 3) stack[sp * NS] = nxt[3], ++sp;
             if (n > 2) stack[sp * NS] = nxt[2], ++sp;
             if (n > 1) stack[sp * NS] = nxt[1], ++sp;
@@ -287,6 +289,7 @@ __device__ __forceinline__ void pool_inst(const DevScene& S, const Pool<F, NS>& 
                 enter = root_box_test<false>(&in->inner_box, n32, no, nd, tmin, tmax, tmin32, tmax32, nullptr);
             if (enter) {
                 if (level == 0) P.st3c(PL::C_WRAY, s, wo), P.st3c(PL::C_WRAY + 3, s, wd);  // the way back to world space
+                NRRT_CHECK(sp < P.cap, "pool traversal stack overflow (level marker)");
                 P.w(PL::W_STACK + sp, s) = NRRT_REF_POP;
                 ++sp;
                 P.set_cur_chain(s, level, ii);
@@ -439,6 +442,8 @@ k_render_pool(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
     P.assign = P.W + (size_t)NS * (PL::W_STACK + stack_cap);
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
     P.cstride = cold_slots;
+    P.cap = stack_cap;
+    NRRT_CHECK((size_t)(gwarp + 1) * NS <= cold_slots, "cold state index");
     P.CD = cold + (size_t)gwarp * NS;
     P.CW = reinterpret_cast<uint32_t*>(cold + (size_t)PL::NCD * cold_slots) + (size_t)gwarp * NS;
     uint32_t segs = 0, paths = 0;
@@ -485,6 +490,9 @@ k_render_pool(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
         const uint32_t n_take = min(best, 32u);
         const bool valid = lane < n_take;
         const uint32_t s = valid ? P.assign[lane] : 0u;
+        NRRT_CHECK(s < NS, "pool slot index");
+        NRRT_CHECK(!valid || (phase == 3 ? ctl_state(P.w(PL::W_CTL, s)) >= PS_HIT : ctl_state(P.w(PL::W_CTL, s)) == phase + 1),
+                   "slot handed to the wrong stage");
         __syncwarp();
         if (phase == 0) pool_node<F, NS>(S, P, s, valid, n_take);
         else if (phase == 1) pool_prim<F, NS>(S, P, s, valid);

@@ -36,6 +36,20 @@
 #define NRRT_STACK_CAP 32          // traversal stack entries per thread (host validates max_stack)
 #endif
 #define NRRT_REF_POP 0xC0000000u   // type 6: "leave instance level" marker on the stack
+// Checked build (-DNRRT_CHECKED=1, tools/build_variant.py): every traversal-stack push, slot index and scene index the
+// kernels form is bounds-checked on the device and a violation aborts the launch (printf + trap), so a test run of the
+// checked library fails loudly.  The stand-in for compute-sanitizer memcheck, which is closed on the GPU pool.
+#if defined(NRRT_CHECKED) && NRRT_CHECKED
+#define NRRT_CHECK(cond, what)                                                                         \
+    do {                                                                                               \
+        if (!(cond)) {                                                                                 \
+            printf("NRRT_CHECK failed: %s (%s:%d) block %d thread %d\n", what, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+            __trap();                                                                                  \
+        }                                                                                              \
+    } while (0)
+#else
+#define NRRT_CHECK(cond, what) do { } while (0)
+#endif
 #define NRRT_INF __longlong_as_double(0x7ff0000000000000LL)
 
 // --------------------------------------------------------------------------- device scene
@@ -69,7 +83,7 @@ struct DevScene {
     const uint2* image_size;
     const uint8_t* perm;            // noise permutation tables, 256 B per (texture, octave)
     const uint32_t* perm_base;      // per texture: first table index
-    uint32_t n_nodes, n_spheres, n_planes, n_instances, n_materials, n_textures;
+    uint32_t n_nodes, n_wnodes, n_spheres, n_planes, n_instances, n_materials, n_textures;
 };
 
 // --------------------------------------------------------------------------- exact f64 helpers
@@ -227,6 +241,7 @@ __device__ __forceinline__ d3 sphere_center(const DevScene& S, uint32_t i, d3 c,
 template <uint32_t F = NRRT_F_ALL>
 __device__ __forceinline__ double sphere_t(const DevScene& S, uint32_t i, d3 o, d3 d, double tmin, double tmax,
                                            double time) {
+    NRRT_CHECK(i < S.n_spheres, "sphere index");
     const f64x4 rec = ldg256d(S.sphere_rec + 4 * (size_t)i);
     d3 c = sphere_center<F>(S, i, mk3(rec.v[0], rec.v[1], rec.v[2]), time);
     double r = rec.v[3];
@@ -250,6 +265,7 @@ __device__ __forceinline__ double sphere_t(const DevScene& S, uint32_t i, d3 o, 
 __device__ __forceinline__ double plane_t(const DevScene& S, uint32_t i, d3 o, d3 d, double tmin, double tmax,
                                           double tbest, double* alpha_out, double* beta_out, d3* point_out) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    NRRT_CHECK(i < S.n_planes, "plane index");
     const double* rec = S.plane_rec + 16 * (size_t)i;
     const f64x4 q0 = ldg256d(rec);  // normal xyz, d
     d3 n = mk3(q0.v[0], q0.v[1], q0.v[2]);
@@ -400,6 +416,7 @@ template <bool VISIT_ALL, bool COUNT, class LoadRay>
 __device__ __forceinline__ uint32_t wide_visit(const DevScene& S, const Ray32& r32, float tmin32, float tmax32,
                                                float tcull, uint32_t ni, double tmin, double tmax, LoadRay&& load_exact_ray,
                                                TraceCounters* cnt, uint32_t (&out)[4]) {
+    NRRT_CHECK(ni < S.n_wnodes, "wide node index");
     const float4* np = S.wnodes + 8 * (size_t)ni;
     const f32x8 A = ldg256(np), B = ldg256(np + 2), C = ldg256(np + 4);  // lo x,y | lo z, hi x | hi y,z
     const uint4 CH = __ldg(reinterpret_cast<const uint4*>(np + 6));
@@ -691,6 +708,7 @@ struct Traversal {
                 S, r32, tmin32, tmax32, tcull, NRRT_REF_INDEX(cur), tmin, tmax,
                 [&](d3& oo, d3& dd) { load_ray(ctx, oo, dd); }, cnt, nxt);
             // continue with the nearest slot, the others wait on the stack (farthest at the bottom)
+            NRRT_CHECK(sp + (n ? n - 1 : 0) <= NRRT_STACK_CAP, "traversal stack overflow");
             if (n > 3) stack[sp * sstride] = nxt[3], ++sp;
             if (n > 2) stack[sp * sstride] = nxt[2], ++sp;
             if (n > 1) stack[sp * sstride] = nxt[1], ++sp;
@@ -778,6 +796,7 @@ struct Traversal {
                 if (NRRT_REF_TYPE(inner) == NRRT_REF_NODE)
                     enter = root_box_test<COUNT>(&in->inner_box, n32, no, nd, tmin, tmax, tmin32, tmax32, cnt);
                 if (enter) {
+                    NRRT_CHECK(sp < NRRT_STACK_CAP, "traversal stack overflow (level marker)");
                     stack[sp * sstride] = NRRT_REF_POP;
                     ++sp;
                     cur_inst.set(level, ii);
@@ -1093,6 +1112,7 @@ __device__ __forceinline__ d3 texture_color(const DevScene& S, uint32_t tex, dou
 template <uint32_t F = NRRT_F_ALL>
 __device__ __forceinline__ bool shade_hit(const DevScene& S, const HitRec& h, d3 rd, bool primary, const Sampler& smp,
                                           uint32_t stage, d3& emitted, d3& atten, d3& new_dir) {
+    NRRT_CHECK(h.material < S.n_materials, "material index");
     const nrrt_material* m = &S.materials[h.material];
     uint32_t kind = m->kind;
     emitted = mk3(0.0, 0.0, 0.0);

@@ -541,6 +541,10 @@ using IdMap = std::map<std::string, uint32_t>;
 struct Builder {
     Graph& g;
     std::string base_dir;
+    // scene files being loaded right now, outermost first: a `Scene { path }` object that names one of them (itself,
+    // or a file that includes it) would recurse until the native stack overflows — the reference does the same
+    // (scene_config.rs:335-340) and dies of it; here it is an error the caller gets back
+    std::vector<std::string> include_stack;
 
     std::string resolve(const std::string& p) const {
         if (!p.empty() && p[0] == '/') return p;
@@ -729,8 +733,15 @@ struct Builder {
             uint32_t m = mat();
             ValuePtr pv = p->get("path");
             if (!pv || pv->kind != Value::String) fail("Scene.path: expected a string");
-            ValuePtr sub = load_scene_file(resolve(pv->s));
-            return build_aux(*sub, true, m);
+            const std::string file = resolve(pv->s);
+            for (const std::string& open_file : include_stack)
+                if (open_file == file) fail("recursive scene include: " + file);
+            if (include_stack.size() >= 16) fail("scene includes nested deeper than 16 files: " + file);
+            ValuePtr sub = load_scene_file(file);
+            include_stack.push_back(file);
+            const uint32_t obj = build_aux(*sub, true, m);
+            include_stack.pop_back();
+            return obj;
         }
         if (kind == "Ref") {
             ValuePtr id = p->get("id");
@@ -890,6 +901,7 @@ nrrt_loaded_scene* nrrt_load_scene(const char* path, const char* base_dir) {
         auto ls = std::make_unique<nrrt_loaded_scene>();
         ValuePtr root = load_scene_file(path);
         Builder b{ls->g, base_dir ? std::string(base_dir) : std::string()};
+        b.include_stack.push_back(path);
         ls->g.root = b.build_aux(*root, false, 0);
         read_camera(*root, ls->cam);
         Graph& g = ls->g;

@@ -346,8 +346,17 @@ class _Builder:
         if kind == "Scene":
             m = mat()
             sub_path = self.resolve(str(p.get("path")))
+            stack = self.__dict__.setdefault("_include_stack", [])
+            if sub_path in stack:
+                raise SceneError(f"recursive scene include: {sub_path}")
+            if len(stack) >= 16:
+                raise SceneError(f"scene includes nested deeper than 16 files: {sub_path}")
             sub = load_scene_file(sub_path)
-            return self.build_aux(sub, m)  # scene.objects: a BVH (= GROUP)
+            stack.append(sub_path)
+            try:
+                return self.build_aux(sub, m)  # scene.objects: a BVH (= GROUP)
+            finally:
+                stack.pop()
         if kind == "Ref":
             rid = p.get("id")
             if rid not in instances:

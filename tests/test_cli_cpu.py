@@ -33,6 +33,25 @@ def test_usage_and_argument_errors(tmp_path):
         assert r.returncode != 0 and needle in (r.stderr + r.stdout), (args, r.stderr, r.stdout)
 
 
+def test_numeric_options_are_validated_like_clap(tmp_path):
+    """Negative, overflowing, fractional or empty numbers are errors (clap's u32 / f64 / u64 parsers), an unknown
+    option is reported without swallowing the argument after it, and nothing is written."""
+    out = str(tmp_path / "n.png")
+    for args, needle in [(("-W", "-1"), "invalid"), (("--width", "4294967296"), "invalid value"),
+                         (("--samples-per-pixel", "1e3"), "invalid value"), (("--ray-max-bounces", ""), "invalid value"),
+                         (("--field-of-view", "wide"), "invalid value"), (("--gamma-value", "x"), "--gamma-value"),
+                         (("--seed", "-3"), "--seed"), (("--device", "zero"), "--device"), (("--gpus", "0"), "--gpus"),
+                         (("--gpus", "two"), "--gpus"), (("--frobnicate", "-W"), "unknown option '--frobnicate'"),
+                         (("-x",), "unknown option '-x'")]:
+        r = run("render", QUADS, "-o", out, *args)
+        assert r.returncode != 0 and needle in (r.stderr + r.stdout), (args, r.stderr, r.stdout)
+        assert not os.path.exists(out)
+    r = run("render", QUADS, "-o", out, env={"NR_RT_GPUS": "many"})
+    assert r.returncode != 0 and "NR_RT_GPUS" in (r.stderr + r.stdout)
+    r = run("render", QUADS, "-o", out, env={"NR_RT_CAMERA_WIDTH": "-5"})
+    assert r.returncode != 0 and "NR_RT_CAMERA_WIDTH" in (r.stderr + r.stdout)
+
+
 def test_output_file_is_not_overwritten_without_force(tmp_path):
     out = tmp_path / "keep.png"
     out.write_bytes(b"precious")

@@ -277,6 +277,40 @@ def test_packed_output_is_the_owned_rows_in_order(gpu_ctx):
     del hs
 
 
+def test_in_library_multi_gpu_render_equals_single_gpu(gpu_ctx, tmp_path):
+    """nrrt_render_multi (one host thread + context per device, rows interleaved, gathered inside the library) gives
+    the single-GPU image bit for bit, into a host image and into a device image on devices[0] (peer copies + placement
+    kernel).  Uses every GPU of the box, and — so that the path is exercised on a one-GPU box too — the same device
+    several times.  The CLI's --gpus writes the same PNG bytes as a single-GPU run."""
+    import subprocess
+    import torch
+    from nr_ray_tracer_b200 import build as B
+    g = load("cornell-teapot-scene.json", width=96, height=55, samples_per_pixel=4)
+    hs = _scene(gpu_ctx, g)
+    cam = api.camera_build(g.camera.to_builder_config())
+    one, st1 = gpu_ctx.render(cam, seed=8)
+    n_gpu = torch.cuda.device_count()
+    for devices in ([0, 0], [0, 0, 0], list(range(n_gpu)) if n_gpu > 1 else [0] * 5):
+        img, st = api.render_multi(devices, hs, cam, seed=8)
+        assert np.array_equal(img, one), devices
+        assert st["segments"] == st1["segments"] and st["paths"] == st1["paths"] and st["pixels"] == 96 * 55
+        dev = torch.full((55, 96, 3), float("nan"), device="cuda:0")
+        api.render_multi(devices, hs, cam, seed=8, out_device_ptr=dev.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(dev.cpu().numpy(), one), devices
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for k, extra in enumerate(([], ["--gpus", str(max(n_gpu, 1))], ["--gpus", "1", "--mode", "fused"])):
+        out = tmp_path / f"g{k}.png"
+        cmd = [B.CLI, "render", "scenes/cornell-box-scene.json", "-W", "64", "-H", "36", "--samples-per-pixel", "4", "-o",
+               str(out), "-v"] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True, cwd=root)
+        assert r.returncode == 0, r.stderr
+        outs.append(out.read_bytes())
+    assert outs[0] == outs[1] == outs[2]
+    del hs
+
+
 def test_full_size_properties_1080p(gpu_ctx):
     """BASELINE size (1920x1080) at low spp: determinism, kernel-design invariance, seed sensitivity,
     non-negativity and the exact path count — properties that do not need the (slow) oracle."""
@@ -295,6 +329,31 @@ def test_full_size_properties_1080p(gpu_ctx):
     # the 64 top-left pixels against the oracle
     ref, _ = O.OracleScene(g).render(O.camera_build(g.camera.to_builder_config()), seed=1, pixel_range=(0, 1920 * 4))
     assert np.allclose(a[:4], ref[:4], rtol=1e-5, atol=1e-7)
+    del hs
+
+
+@pytest.mark.parametrize("name", ["cornell-box-scene.json", "utah-teapot-scene.json", "cornell-teapot-scene.json"])
+def test_full_width_strip_at_baseline_size_matches_oracle(gpu_ctx, name):
+    """BASELINE size (1920x1080, depth 50) at 16 spp: an 8-row strip through the middle of the image (15 360 pixels,
+    245 760 paths) rendered by the oracle with the same Philox streams, against the same rows of the full GPU image,
+    for the product path (MODE_AUTO) and the explicitly pooled kernel.  Same bar as the small same-stream renders:
+    >= 99 % of the pixels equal to 1e-5 relative (only libm-vs-CUDA transcendentals can flip a rare path)."""
+    W, H, spp, y0 = 1920, 1080, 16, 536
+    g = load(name, width=W, height=H, samples_per_pixel=spp, ray_max_bounces=50)
+    hs = _scene(gpu_ctx, g)
+    cam = api.camera_build(g.camera.to_builder_config())
+    ref, cnt = O.OracleScene(g).render(O.camera_build(g.camera.to_builder_config()), seed=21,
+                                       pixel_range=(y0 * W, (y0 + 8) * W))
+    imgs = []
+    for mode in (A.MODE_AUTO, A.MODE_POOL):
+        img, st = gpu_ctx.render(cam, seed=21, mode=mode)
+        assert st["paths"] == W * H * spp
+        strip, want = img[y0:y0 + 8].astype(np.float64), ref[y0:y0 + 8].astype(np.float64)
+        rel = np.abs(strip - want) / np.maximum(1e-3, np.abs(want))
+        assert float((rel <= 1e-5).all(axis=2).mean()) >= 0.99, (name, mode)
+        assert abs(float(strip.mean()) - float(want.mean())) <= 0.01 * float(want.mean()) + 1e-6
+        imgs.append(img)
+    assert np.array_equal(imgs[0], imgs[1])
     del hs
 
 

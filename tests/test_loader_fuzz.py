@@ -90,3 +90,31 @@ def test_heavy_corruption_is_rejected_not_crashed(tmp_path):
             except api.NrrtError:
                 pass
     assert rejected > 200
+
+
+def test_recursive_scene_includes_are_an_error_not_a_crash(tmp_path):
+    """A scene that includes itself — directly or through another file — must come back as a loader error from both
+    loaders (the reference recurses until its stack overflows, scene_config.rs:335-340; the native loader must not take
+    the process down with it)."""
+    from nr_ray_tracer_b200 import api
+    from nr_ray_tracer_b200.scene_config import SceneError, load_scene
+    a, b = tmp_path / "a.json", tmp_path / "b.json"
+    a.write_text('{"camera": {}, "scene": [{"Scene": {"path": "b.json"}}]}')
+    b.write_text('{"camera": {}, "scene": [{"Scene": {"path": "a.json"}}]}')
+    selfinc = tmp_path / "self.json"
+    selfinc.write_text('{"camera": {}, "scene": [{"Sphere": {"center": [0,0,0], "radius": 1}}, {"Scene": {"path": "self.json"}}]}')
+    for f in (a, selfinc):
+        with pytest.raises(api.NrrtError) as e:
+            api.NativeScene(str(f), base_dir=str(tmp_path))
+        assert "include" in str(e.value)
+        with pytest.raises(SceneError):
+            load_scene(str(f), base_dir=str(tmp_path))
+    # a legitimate diamond (two includes of the same file) still loads
+    leaf = tmp_path / "leaf.json"
+    leaf.write_text('{"camera": {}, "scene": [{"Sphere": {"center": [0,0,0], "radius": 1}}]}')
+    top = tmp_path / "top.json"
+    top.write_text('{"camera": {}, "scene": [{"Scene": {"path": "leaf.json"}}, {"Translate": {"offset": [3,0,0], '
+                   '"object": {"Scene": {"path": "leaf.json"}}}}]}')
+    ns = api.NativeScene(str(top), base_dir=str(tmp_path))
+    assert ns.graph.n_objects >= 4
+    assert load_scene(str(top), base_dir=str(tmp_path)).count_primitives() == 2

@@ -1123,6 +1123,26 @@ int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
     UP(sphere_order, sc->sphere_order, sc->n_spheres);
     UP(sphere_object, sc->sphere_object, sc->n_spheres);
     UP(plane_rec, sc->plane_rec, (size_t)sc->n_planes * 16);
+    {   // f32 reject-only records (plane_prereject): A = v x w, B = w x u in f64, then rounded
+        std::vector<float4> p32((size_t)sc->n_planes * 4);
+        for (uint32_t i = 0; i < sc->n_planes; ++i) {
+            const double* r = sc->plane_rec + 16 * (size_t)i;  // normal, d, p, w, u, v
+            const double *n = r, *pp = r + 4, *w = r + 7, *u = r + 10, *v = r + 13;
+            const double A[3] = {v[1] * w[2] - v[2] * w[1], v[2] * w[0] - v[0] * w[2], v[0] * w[1] - v[1] * w[0]};
+            const double B[3] = {w[1] * u[2] - w[2] * u[1], w[2] * u[0] - w[0] * u[2], w[0] * u[1] - w[1] * u[0]};
+            // |A|_1, |B|_1, |p|_inf rounded UP (they scale error bounds)
+            auto up = [](double x) { float f = (float)x; return (double)f < x ? std::nextafterf(f, INFINITY) : f; };
+            float a1 = up(std::fabs(A[0]) + std::fabs(A[1]) + std::fabs(A[2])) * 1.0000002f;
+            const float b1 = up(std::fabs(B[0]) + std::fabs(B[1]) + std::fabs(B[2])) * 1.0000002f;
+            const float pmax = up(std::fmax(std::fmax(std::fabs(pp[0]), std::fabs(pp[1])), std::fabs(pp[2])));
+            if (sc->plane_material[i] & NRRT_PLANE_TRIANGLE_BIT) a1 = -a1;  // sign bit = Triangle (NaN keeps "maybe")
+            p32[4 * (size_t)i + 0] = make_float4((float)n[0], (float)n[1], (float)n[2], (float)r[3]);
+            p32[4 * (size_t)i + 1] = make_float4((float)A[0], (float)A[1], (float)A[2], (float)pp[0]);
+            p32[4 * (size_t)i + 2] = make_float4((float)B[0], (float)B[1], (float)B[2], (float)pp[1]);
+            p32[4 * (size_t)i + 3] = make_float4((float)pp[2], a1, b1, pmax);
+        }
+        UP(plane32, p32.data(), p32.size());
+    }
     UP(plane_material, sc->plane_material, sc->n_planes);
     UP(plane_order, sc->plane_order, sc->n_planes);
     UP(plane_object, sc->plane_object, sc->n_planes);
@@ -1497,10 +1517,21 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     P.key = make_uint2((uint32_t)o.seed, (uint32_t)(o.seed >> 32));
     P.rank = o.rank, P.world = o.world, P.rows_per_block = o.rows_per_block;
     P.n_owned_pixels = owned_rows(H, o.rank, o.world, o.rows_per_block) * W;
-    // chunking depends on spp only (=> the per-pixel sum order, and the image bit for bit, are the same for
-    // every slot count and GPU count): at most 32 chunks per pixel
-    P.chunk = (c.samples_per_pixel + 31) / 32;
-    P.n_chunks = (c.samples_per_pixel + P.chunk - 1) / P.chunk;
+    // Work-item size.  It fixes the order in which a pixel's samples are summed, so it may depend only on what every
+    // rank of every partition agrees on — spp and the size of the WHOLE image — never on slots, rank or world: the
+    // image is then bit-identical for every slot count and GPU count.  An item should be a small fraction (1/16) of
+    // what one path slot gets to do in the whole render, so the tail of the render stays short, but no smaller: each
+    // item costs 24 bytes of scratch that k_resolve reads back.  Sized for up to 16 GPUs x 160 k resident slots; never
+    // more than 32 items per pixel.  (1080p x 1024 spp: 20 items of 52 samples; 4K x 4096 spp: 5 items — 1 GB of
+    // scratch where a fixed 32 needed 6.4 GB.)
+    {
+        const uint64_t spp = c.samples_per_pixel;
+        const uint64_t per_slot = total_pixels * spp / 2560000ull;  // samples one slot traces when 16 GPUs share the image
+        uint64_t chunk = std::max<uint64_t>(per_slot / 16, (spp + 31) / 32);
+        chunk = std::min<uint64_t>(std::max<uint64_t>(chunk, 1), spp);
+        P.chunk = (uint32_t)chunk;
+        P.n_chunks = (uint32_t)((spp + chunk - 1) / chunk);
+    }
     const uint64_t n_items64 = (uint64_t)P.n_owned_pixels * P.n_chunks;
     if (n_items64 > 0xFFFFFFF0ull) {
         ctx->err = "too many work items";
@@ -1586,6 +1617,15 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         o_q0 = carve(n * sizeof(uint32_t));
         o_q1 = carve(n * sizeof(uint32_t));
         o_cnt = carve(8 * sizeof(uint32_t));
+    }
+    if (off > ctx->scratch_bytes) {  // say what is needed instead of failing inside cudaMalloc
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && off > free_b + ctx->scratch_bytes) {
+            ctx->err = "nrrt_render: needs " + std::to_string(off >> 20) + " MiB of device scratch (" +
+                       std::to_string(P.n_items) + " work items x 24 B + framebuffer), " +
+                       std::to_string((free_b + ctx->scratch_bytes) >> 20) + " MiB available";
+            return NRRT_ERR_LIMIT;
+        }
     }
     int rc = ensure_scratch(ctx, std::max<size_t>(off, 256));
     if (rc != NRRT_OK) return rc;

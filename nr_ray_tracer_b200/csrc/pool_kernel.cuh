@@ -28,6 +28,9 @@
                                    // 3720, 1/2 2091 / 1949 / 3786.  Slots per warp: 48 1665, 56 1946, 64 2031, 80 1860.
 #endif
 #define NRRT_POOL_TRIVIAL_MAX 4     // camera rays that miss the scene's root box, absorbed per SHADE visit
+#ifndef NRRT_POOL_SCREEN_MIN
+#define NRRT_POOL_SCREEN_MIN 8      // NODE stage: lanes holding a plane leaf before the reject-only test runs for them
+#endif
 
 enum : uint32_t {
     PS_RETIRED = 0,
@@ -126,11 +129,23 @@ __device__ __forceinline__ uint32_t ctl_sp(uint32_t c) { return (c >> 10) & 255u
 __device__ __forceinline__ uint32_t ctl_make(uint32_t state, uint32_t level, uint32_t bdepth, uint32_t sp) {
     return state | (level << 4) | (bdepth << 7) | (sp << 10);
 }
-// the stage a slot waits for, from the entry it holds
-__device__ __forceinline__ uint32_t classify_ref(uint32_t cur) {
+#ifndef NRRT_POOL_PREREJECT
+#define NRRT_POOL_PREREJECT 0  // f32 reject-only plane test (plane_prereject) before the exact one:
+                               // 0 = off, 1 = inside the NODE stage (a rejected leaf never reaches PRIM), 2 = at the top of PRIM.
+                               // Proven sound by the checked build (27 M segments, no hit ever rejected) and measured on B200
+                               // (teapot / C5 / Cornell, Mrays/s): off 2116 / 1959 / 3787, NODE stage 2020 / 1779 / 3059,
+                               // PRIM stage 2098 / 1887 / 3597 (profiles/r02_pool_variants3.log).  It does not pay: the exact
+                               // test already leaves after one dot product and one division when t > best t, the FP64 pipe
+                               // is 6 % busy, and what a PRIM visit costs is its scheduling round, not its arithmetic.
+#endif
+// the stage a slot waits for, from the entry it holds.  With the reject-only plane test a plane leaf first waits for
+// the NODE stage (which runs that test) and only one that survived it (`screened`) waits for the PRIM stage.
+template <uint32_t F>
+__device__ __forceinline__ uint32_t classify_ref(uint32_t cur, bool screened = false) {
     const uint32_t ty = NRRT_REF_TYPE(cur);
     if (ty == NRRT_REF_NODE) return PS_NODE;
-    if (ty == NRRT_REF_SPHERE || ty == NRRT_REF_PLANE) return PS_PRIM;
+    if (ty == NRRT_REF_PLANE) return (NRRT_POOL_PREREJECT == 1 && (F & NRRT_F_PLANES) && !screened) ? PS_NODE : PS_PRIM;
+    if (ty == NRRT_REF_SPHERE) return PS_PRIM;
     if (cur == NRRT_REF_NONE) return PS_HIT;
     return PS_INST;  // instance leaf or NRRT_REF_POP
 }
@@ -159,14 +174,18 @@ __device__ __forceinline__ uint32_t pool_begin(const DevScene& S, const Pool<F, 
     return cur;
 }
 
-// ---- NODE stage
+// ---- NODE stage.  A lane walks inner nodes; when it lands on a plane leaf it runs the f32 reject-only test right
+// here (plane_prereject) and, if that proves a miss, takes the next stack entry and goes on — four out of five
+// primitive tests on a mesh end this way, without a visit to the PRIM stage.
 template <uint32_t F, int NS>
 __device__ __forceinline__ void pool_node(const DevScene& S, const Pool<F, NS>& P, uint32_t s, bool valid,
                                           uint32_t n_take) {
     using PL = Pool<F, NS>;
+    constexpr bool kPre = NRRT_POOL_PREREJECT == 1 && (F & NRRT_F_PLANES) != 0;
     const float tmin32 = 0.001f, tmax32 = 3.4e38f;
     uint32_t ctl = 0, cur = NRRT_REF_NONE, sp = 0;
     Ray32 r32{};
+    Ray32P rp{};
     float tcull = 0.f;
     if (valid) {
         ctl = P.w(PL::W_CTL, s);
@@ -174,15 +193,27 @@ __device__ __forceinline__ void pool_node(const DevScene& S, const Pool<F, NS>& 
         sp = ctl_sp(ctl);
         r32 = P.ld_r32(s);
         tcull = __uint_as_float(P.w(PL::W_TCULL, s));
+        if (kPre) {
+            d3 o, d;
+            P.ld_ray(s, o, d);
+            rp = make_ray32p(o, d);
+        }
     }
     const uint32_t level = ctl_level(ctl);
     uint32_t* stack = &P.w(PL::W_STACK, s);
     const uint32_t keep = max(1u, (n_take * NRRT_POOL_NODE_KEEP_NUM) / NRRT_POOL_NODE_KEEP_DEN);
+    bool tested = false;  // the plane leaf in hand has been through the reject test ("maybe": it needs the exact one)
     for (uint32_t it = 0;; ++it) {
         const bool at_node = valid && NRRT_REF_TYPE(cur) == NRRT_REF_NODE;
-        const uint32_t n_act = __popc(__ballot_sync(0xffffffffu, at_node));
+        const bool at_plane = kPre && valid && !tested && NRRT_REF_TYPE(cur) == NRRT_REF_PLANE;
+        const unsigned m_node = __ballot_sync(0xffffffffu, at_node);
+        const unsigned m_plane = kPre ? __ballot_sync(0xffffffffu, at_plane) : 0u;
+        const uint32_t n_act = __popc(m_node | m_plane);
         if (n_act == 0 || (it && n_act < keep)) break;
-        if (at_node) {
+        // one kind of work per trip, chosen for the whole warp: lanes holding a plane leaf wait until enough of them
+        // do (or nobody has a node left), so neither code path runs for a lane or two
+        const bool screen = kPre && (__popc(m_plane) >= NRRT_POOL_SCREEN_MIN || m_node == 0u);
+        if (!screen && at_node) {
             uint32_t nxt[4];
             const uint32_t n = wide_visit<false, false>(
                 S, r32, tmin32, tmax32, tcull, NRRT_REF_INDEX(cur), 0.001, NRRT_INF,
@@ -196,11 +227,27 @@ __device__ __forceinline__ void pool_node(const DevScene& S, const Pool<F, NS>& 
                 cur = NRRT_REF_NONE;
                 if (sp) --sp, cur = stack[sp * NS];
             }
+        } else if (screen && at_plane) {
+            if (plane_prereject(S, NRRT_REF_INDEX(cur), rp, 0.000999f, tcull)) {
+#if defined(NRRT_CHECKED) && NRRT_CHECKED
+                {   // the reject-only test may only reject what the exact test rejects
+                    d3 xo, xd, xp;
+                    double xa, xb;
+                    P.ld_ray(s, xo, xd);
+                    const double xt = plane_t(S, NRRT_REF_INDEX(cur), xo, xd, 0.001, NRRT_INF, P.d(PL::D_BT, s), &xa, &xb, &xp);
+                    NRRT_CHECK(!(xt == xt), "plane_prereject rejected a primitive the exact test accepts");
+                }
+#endif
+                cur = NRRT_REF_NONE;
+                if (sp) --sp, cur = stack[sp * NS];
+            } else {
+                tested = true;
+            }
         }
     }
     if (valid) {
         P.w(PL::W_CUR, s) = cur;
-        P.w(PL::W_CTL, s) = ctl_make(classify_ref(cur), level, ctl_bdepth(ctl), sp);
+        P.w(PL::W_CTL, s) = ctl_make(classify_ref<F>(cur, tested), level, ctl_bdepth(ctl), sp);
     }
 }
 
@@ -222,6 +269,13 @@ __device__ __forceinline__ void pool_prim(const DevScene& S, const Pool<F, NS>& 
     if ((F & NRRT_F_SPHERES) && (!(F & NRRT_F_PLANES) || NRRT_REF_TYPE(leaf) == NRRT_REF_SPHERE)) {
         t = sphere_t<F>(S, NRRT_REF_INDEX(leaf), o, d, tmin, tmax, PL::kMotion ? P.cd(PL::C_TIME, s) : 0.0);
         pt = ray_at(o, d, t);
+    } else if (NRRT_POOL_PREREJECT == 2 &&
+               plane_prereject(S, NRRT_REF_INDEX(leaf), make_ray32p(o, d), 0.000999f, __uint_as_float(P.w(PL::W_TCULL, s)))) {
+        t = __longlong_as_double(0x7ff8000000000000LL);  // proven miss: the exact test would return None
+#if defined(NRRT_CHECKED) && NRRT_CHECKED
+        const double xt = plane_t(S, NRRT_REF_INDEX(leaf), o, d, tmin, tmax, best_t, &a_, &b_, &pt);
+        NRRT_CHECK(!(xt == xt), "plane_prereject rejected a primitive the exact test accepts");
+#endif
     } else {
         t = plane_t(S, NRRT_REF_INDEX(leaf), o, d, tmin, tmax, best_t, &a_, &b_, &pt);
     }
@@ -250,7 +304,7 @@ __device__ __forceinline__ void pool_prim(const DevScene& S, const Pool<F, NS>& 
     uint32_t cur = NRRT_REF_NONE;
     if (sp) --sp, cur = P.w(PL::W_STACK + sp, s);
     P.w(PL::W_CUR, s) = cur;
-    P.w(PL::W_CTL, s) = ctl_make(classify_ref(cur), level, bdepth, sp);
+    P.w(PL::W_CTL, s) = ctl_make(classify_ref<F>(cur), level, bdepth, sp);
 }
 
 // ---- INST stage: enter a wrapper chain, or leave one (level marker)
@@ -297,7 +351,7 @@ __device__ __forceinline__ void pool_inst(const DevScene& S, const Pool<F, NS>& 
                 P.st_ray(s, no, nd);
                 P.st_r32(s, n32);
                 P.w(PL::W_CUR, s) = inner;
-                P.w(PL::W_CTL, s) = ctl_make(classify_ref(inner), level, ctl_bdepth(ctl), sp);
+                P.w(PL::W_CTL, s) = ctl_make(classify_ref<F>(inner), level, ctl_bdepth(ctl), sp);
                 return;
             }
         }
@@ -305,7 +359,7 @@ __device__ __forceinline__ void pool_inst(const DevScene& S, const Pool<F, NS>& 
     cur = NRRT_REF_NONE;
     if (sp) --sp, cur = P.w(PL::W_STACK + sp, s);
     P.w(PL::W_CUR, s) = cur;
-    P.w(PL::W_CTL, s) = ctl_make(classify_ref(cur), level, ctl_bdepth(ctl), sp);
+    P.w(PL::W_CTL, s) = ctl_make(classify_ref<F>(cur), level, ctl_bdepth(ctl), sp);
 }
 
 // ---- SHADE stage: shade a finished query, account finished paths, next camera ray / work item, start the next query
@@ -396,7 +450,7 @@ __device__ __forceinline__ void pool_shade(const DevScene& S, const nrrt_camera&
         if (!start) break;
         cur = pool_begin<F, NS>(S, P, s, o, d);
         ++segs;
-        state = classify_ref(cur);
+        state = classify_ref<F>(cur);
         // A camera ray that misses the scene's root box is a finished path on the spot (every other camera ray of an
         // object in front of a background): account for it here instead of spending another SHADE visit on it.
         if (cur != NRRT_REF_NONE || bounce != 0 || rep >= NRRT_POOL_TRIVIAL_MAX) break;

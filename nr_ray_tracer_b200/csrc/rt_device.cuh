@@ -70,6 +70,7 @@ struct DevScene {
     const uint32_t* sphere_order;
     const uint32_t* sphere_object;
     const double* plane_rec;   // [n][16]: normal xyz, d, p xyz, w xyz, u xyz, v xyz (one 128-byte line)
+    const float4* plane32;     // [n][4]: the f32 reject-only view of the same planes (plane_prereject), built at upload
     const uint32_t* plane_material;
     const uint32_t* plane_order;
     const uint32_t* plane_object;
@@ -291,6 +292,61 @@ __device__ __forceinline__ double plane_t(const DevScene& S, uint32_t i, d3 o, d
     *beta_out = beta;
     *point_out = point;
     return t;
+}
+
+// --------------------------------------------------------------------------- f32 reject-only plane test
+// Plane::hit (plane.rs:141-174) evaluated in f32 with a running error bound, used ONLY to prove a miss: when the bound
+// shows that t lies outside [tmin, best t] or that alpha / beta lie outside the primitive, the exact f64 test would
+// return None as well and is skipped; everything else ("maybe") goes to the exact test, which alone decides hits and
+// produces t, alpha, beta.  Like the f32 box filter, it can only save work, never change a result.
+//
+// Record (4 x float4, built at upload from the f64 record): normal xyz, d | A xyz, p.x | B xyz, p.y | p.z, +-|A|_1,
+// |B|_1, |p|_inf, with A = v x w and B = w x u so that alpha = q.A and beta = q.B (w.(q x v) = q.(v x w),
+// w.(u x q) = q.(w x u)); the sign of the |A|_1 word carries the Triangle flag.
+// Error model (u = 2^-24): inputs are f64 values rounded to f32, every bound below uses 16u per rounding step where
+// first-order analysis needs at most 5u, plus an absolute 1e-6 on t (relative) and on the barycentrics, which also
+// swallows the f64 rounding of the reference's own evaluation (1e-15).  NaN / inf anywhere make every comparison
+// false, i.e. "maybe".
+struct Ray32P {
+    float ox, oy, oz, dx, dy, dz;
+    float omax, dmax;  // |o|_inf, |d|_inf
+};
+__device__ __forceinline__ Ray32P make_ray32p(d3 o, d3 d) {
+    Ray32P r;
+    r.ox = (float)o.x, r.oy = (float)o.y, r.oz = (float)o.z;
+    r.dx = (float)d.x, r.dy = (float)d.y, r.dz = (float)d.z;
+    r.omax = fmaxf(fmaxf(fabsf(r.ox), fabsf(r.oy)), fabsf(r.oz));
+    r.dmax = fmaxf(fmaxf(fabsf(r.dx), fabsf(r.dy)), fabsf(r.dz));
+    return r;
+}
+#define NRRT_P32_U 9.5367431640625e-07f  // 16 * 2^-24
+// true = the exact test is certain to return None
+__device__ __forceinline__ bool plane_prereject(const DevScene& S, uint32_t i, const Ray32P& r, float tmin_lo, float tcull) {
+    const float4* rec = S.plane32 + 4 * (size_t)i;
+    const f32x8 a = ldg256(rec), b = ldg256(rec + 2);
+    const float nx = a.v[0], ny = a.v[1], nz = a.v[2], D = a.v[3];
+    const float Ax = a.v[4], Ay = a.v[5], Az = a.v[6], px = a.v[7];
+    const float Bx = b.v[0], By = b.v[1], Bz = b.v[2], py = b.v[3];
+    const float pz = b.v[4], a1s = b.v[5], b1 = b.v[6], pmax = b.v[7];
+    const float den = fmaf(nx, r.dx, fmaf(ny, r.dy, nz * r.dz));
+    const float e_den = NRRT_P32_U * 1.75f * r.dmax;  // |n|_1 <= sqrt(3): the normal is unit length
+    if (!(fabsf(den) > 2.0f * e_den)) return false;
+    const float num = D - fmaf(nx, r.ox, fmaf(ny, r.oy, nz * r.oz));
+    const float e_num = NRRT_P32_U * (fabsf(D) + 1.75f * r.omax);
+    const float rden = 1.0f / den;
+    const float t = num * rden, at = fabsf(t);
+    // |den_true| >= |den| - e_den >= |den| / 2
+    const float e_t = 2.0f * fabsf(rden) * fmaf(at, e_den, e_num) + (NRRT_P32_U + 1e-6f) * at;
+    if (t - e_t > tcull || t + e_t < tmin_lo) return true;  // t > best t (strictly), or t < tmin
+    const float scale = fmaf(at, r.dmax, r.omax + pmax);
+    const float e_q = fmaf(NRRT_P32_U, scale, r.dmax * e_t);
+    const float qx = fmaf(t, r.dx, r.ox) - px, qy = fmaf(t, r.dy, r.oy) - py, qz = fmaf(t, r.dz, r.oz) - pz;
+    const float alpha = fmaf(qx, Ax, fmaf(qy, Ay, qz * Az)), beta = fmaf(qx, Bx, fmaf(qy, By, qz * Bz));
+    // each q_i is off by at most e_q, the dot product adds 3 roundings of terms bounded by scale * |A|_inf
+    const float e_a = fmaf(fabsf(a1s), e_q + NRRT_P32_U * scale, 1e-6f), e_b = fmaf(b1, e_q + NRRT_P32_U * scale, 1e-6f);
+    if (alpha + e_a < 0.0f || beta + e_b < 0.0f || alpha - e_a > 1.0f || beta - e_b > 1.0f) return true;
+    if (__float_as_uint(a1s) >> 31) return (alpha + beta) - (e_a + e_b) > 1.0f;  // Triangle: alpha + beta < 1
+    return false;
 }
 
 // --------------------------------------------------------------------------- closest hit

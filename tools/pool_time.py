@@ -7,7 +7,7 @@ from nr_ray_tracer_b200 import _abi as A, api  # noqa: E402
 from nr_ray_tracer_b200.scene_config import CameraConfig, load_scene  # noqa: E402
 
 modes = sys.argv[1:] or ["pool"]
-M = {"pool": A.MODE_POOL, "fused": A.MODE_FUSED, "wavefront": A.MODE_WAVEFRONT, "mega": A.MODE_MEGAKERNEL}
+M = {"auto": A.MODE_AUTO, "pool": A.MODE_POOL, "fused": A.MODE_FUSED, "wavefront": A.MODE_WAVEFRONT, "mega": A.MODE_MEGAKERNEL}
 ctx = api.Context(0)
 out = []
 for name, spp in (("utah-teapot-scene.json", 64), ("cornell-teapot-scene.json", 32), ("cornell-box-scene.json", 64),

@@ -310,7 +310,11 @@ __global__ void k_encode_rgb8(const float* __restrict__ rgb, size_t n, float gam
 // through HBM and there is no queue, no compaction and a single launch.  Traversal and shading use the same device functions as the
 // wavefront kernels and the same (pixel, sample-chunk) work items, so the image is bit-identical.
 #ifndef NRRT_FUSED_MIN
-#define NRRT_FUSED_MIN 16
+#define NRRT_FUSED_MIN 24  // lanes of a warp that must be waiting before a shading round runs.  Measured on B200, round 2
+                           // (Cornell / spheres / noise / earth, Mrays/s; profiles/r02_fused_quorum_sweep.log): 16 6173 / 4558 /
+                           // 5009 / 10745, 20 6250 / 4645 / 5334 / -, 24 6251 / 4671 / 5539 / 11622, 28 6053 / 4646 / 5596 /
+                           // 11929, 32 5486 / 4405 / 5651 / 11875.  (The mesh scenes, which preferred 16-20 in this kernel,
+                           // are rendered by the pooled kernel under NRRT_MODE_AUTO.)
 #endif
 #define NRRT_FUSED_STATE_DOUBLES 27  // o(3) d(3) T(3) sum(3) | attr: p(3) alpha beta dobj(3) | object-space ray (6) | time
 #ifndef NRRT_FUSED_BLOCKS_PER_SM
@@ -780,6 +784,8 @@ struct nrrt_ctx {
     uint32_t features = NRRT_F_ALL;    // NRRT_F_* mask of the uploaded scene
     double trace_time = 0.0;           // Ray::time of nrrt_trace_rays queries
     bool speculate = false;            // fused kernel: speculative traversal (deep trees only)
+    bool has_binary = false;           // the scene also went up in binary-node form (small trees)
+    uint32_t binary_stack = 0;         // traversal stack need over the binary nodes
     cudaStream_t side = nullptr;       // progress polling while a single-launch render runs (created on first use)
     void* enc_buf = nullptr;           // output-stage scratch (nrrt_encode_rgb8), grown on demand
     size_t enc_bytes = 0;
@@ -1255,6 +1261,8 @@ int nrrt_scene_upload(nrrt_ctx* ctx, const nrrt_scene_desc* sc) {
         ctx->speculate = sc->n_nodes >= NRRT_BINARY_MAX_NODES;
         if (const char* e = std::getenv("NRRT_SPECULATE")) ctx->speculate = std::atoi(e) != 0;  // developer override
         if (!binary_ok) ctx->speculate = true;  // the plain instantiation walks the binary nodes
+        ctx->has_binary = binary_ok;
+        ctx->binary_stack = binary_ok ? binary_stack_need(sc) + 2 : 0;
     }
     ctx->dev = D;
     ctx->max_stack = sc->max_stack;
@@ -1331,12 +1339,15 @@ struct PoolPlan {
     size_t smem = 0, cold_bytes_per_slot = 0;
     uint32_t cap = 0;
     uint64_t slots = 0;  // resident path slots on the whole GPU
+    bool lite = false;   // the two-stage variant for small scenes (binary nodes, lane-owned traversal)
 };
-template <uint32_t F>
+template <uint32_t F, bool LITE>
 static PoolPlan pool_plan_f(const nrrt_ctx* ctx) {
-    using PL = Pool<F, NRRT_POOL_NS>;
+    using PL = Pool<F, NRRT_POOL_NS, LITE>;
     PoolPlan best;
-    best.cap = std::min<uint32_t>(NRRT_STACK_CAP, (std::max<uint32_t>(ctx->max_stack, 4u) + 3u) & ~3u);
+    best.lite = LITE;
+    // (LITE walks the binary nodes: their stack need is what nrrt_scene_upload computed for them)
+    best.cap = std::min<uint32_t>(NRRT_STACK_CAP, (std::max<uint32_t>(LITE ? ctx->binary_stack : ctx->max_stack, 4u) + 3u) & ~3u);
     best.cold_bytes_per_slot = PL::cold_bytes_per_slot();
     const size_t bpw = PL::bytes_per_warp(best.cap);
     unsigned best_warps = 0;
@@ -1348,11 +1359,11 @@ static PoolPlan pool_plan_f(const nrrt_ctx* ctx) {
         if (smem + NRRT_POOL_STATIC_SMEM > ctx->smem_per_block) continue;
         // (the attribute is a per-function limit shared by every host thread: always the device maximum, never a
         // per-launch value another thread's launch could find lowered — nrrt_render_multi renders from several threads)
-        if (cudaFuncSetAttribute(k_render_pool<F, NRRT_POOL_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(k_render_pool<F, NRRT_POOL_NS, LITE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)ctx->smem_per_block - NRRT_POOL_STATIC_SMEM) != cudaSuccess)
             continue;
         int blocks = 0;  // resident blocks per SM: shared memory AND registers
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_render_pool<F, NRRT_POOL_NS>, (int)wpb * 32, smem) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_render_pool<F, NRRT_POOL_NS, LITE>, (int)wpb * 32, smem) != cudaSuccess)
             continue;
         if ((unsigned)blocks * wpb > best_warps) {
             best_warps = (unsigned)blocks * wpb;
@@ -1363,14 +1374,16 @@ static PoolPlan pool_plan_f(const nrrt_ctx* ctx) {
     best.slots = (uint64_t)ctx->sms * best_warps * NRRT_POOL_NS;
     return best;
 }
-static PoolPlan pool_plan(const nrrt_ctx* ctx) {
+static PoolPlan pool_plan(const nrrt_ctx* ctx, bool lite) {
+#define NRRT_POOL_PLAN(FEAT) return lite ? pool_plan_f<FEAT, true>(ctx) : pool_plan_f<FEAT, false>(ctx);
     switch (ctx->features) {
-        case NRRT_F_CORNELL: return pool_plan_f<NRRT_F_CORNELL>(ctx);
-        case NRRT_F_BALLS: return pool_plan_f<NRRT_F_BALLS>(ctx);
-        case NRRT_F_BALLS_TEX: return pool_plan_f<NRRT_F_BALLS_TEX>(ctx);
-        case NRRT_F_GENERAL: return pool_plan_f<NRRT_F_GENERAL>(ctx);
-        default: return pool_plan_f<NRRT_F_ALL>(ctx);
+        case NRRT_F_CORNELL: NRRT_POOL_PLAN(NRRT_F_CORNELL)
+        case NRRT_F_BALLS: NRRT_POOL_PLAN(NRRT_F_BALLS)
+        case NRRT_F_BALLS_TEX: NRRT_POOL_PLAN(NRRT_F_BALLS_TEX)
+        case NRRT_F_GENERAL: NRRT_POOL_PLAN(NRRT_F_GENERAL)
+        default: NRRT_POOL_PLAN(NRRT_F_ALL)
     }
+#undef NRRT_POOL_PLAN
 }
 static unsigned pool_blocks(const PoolPlan& pl, uint32_t n_slots) {
     const unsigned per_block = pl.warps_per_block * NRRT_POOL_NS;
@@ -1382,12 +1395,18 @@ static cudaError_t launch_pool(nrrt_ctx* ctx, const PoolPlan& pl, const nrrt_cam
     const unsigned blocks = pool_blocks(pl, P.n_slots);
     const uint32_t cold_slots = blocks * pl.warps_per_block * NRRT_POOL_NS;
     cudaError_t e = cudaSuccess;
-#define NRRT_POOL_LAUNCH(FEAT)                                                                                            \
-    e = cudaFuncSetAttribute(k_render_pool<FEAT, NRRT_POOL_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+#define NRRT_POOL_LAUNCH_L(FEAT, LITE)                                                                                    \
+    e = cudaFuncSetAttribute(k_render_pool<FEAT, NRRT_POOL_NS, LITE>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                              (int)ctx->smem_per_block - NRRT_POOL_STATIC_SMEM);                                           \
     if (e == cudaSuccess)                                                                                                 \
-        k_render_pool<FEAT, NRRT_POOL_NS><<<blocks, pl.warps_per_block * 32, pl.smem, ctx->stream>>>(                     \
+        k_render_pool<FEAT, NRRT_POOL_NS, LITE><<<blocks, pl.warps_per_block * 32, pl.smem, ctx->stream>>>(               \
             ctx->dev, c, P, partials, ctx->d_counters, pl.cap, cold, cold_slots);
+#define NRRT_POOL_LAUNCH(FEAT)                                                                                            \
+    if (pl.lite) {                                                                                                        \
+        NRRT_POOL_LAUNCH_L(FEAT, true)                                                                                    \
+    } else {                                                                                                              \
+        NRRT_POOL_LAUNCH_L(FEAT, false)                                                                                   \
+    }
     switch (ctx->features) {
         case NRRT_F_CORNELL: NRRT_POOL_LAUNCH(NRRT_F_CORNELL) break;
         case NRRT_F_BALLS: NRRT_POOL_LAUNCH(NRRT_F_BALLS) break;
@@ -1395,6 +1414,7 @@ static cudaError_t launch_pool(nrrt_ctx* ctx, const PoolPlan& pl, const nrrt_cam
         case NRRT_F_GENERAL: NRRT_POOL_LAUNCH(NRRT_F_GENERAL) break;
         default: NRRT_POOL_LAUNCH(NRRT_F_ALL) break;
     }
+#undef NRRT_POOL_LAUNCH_L
 #undef NRRT_POOL_LAUNCH
     return e;
 }
@@ -1574,7 +1594,10 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
 
     PoolPlan plan;
     if (pooled) {  // persistent: every resident pool slot starts with one item; the work counter hands out the rest
-        plan = pool_plan(ctx);
+        // small scenes (binary nodes on the device): the two-stage variant
+        bool lite = ctx->has_binary;
+        if (const char* e = std::getenv("NRRT_POOL_LITE")) lite = std::atoi(e) != 0 && ctx->has_binary;  // developer override
+        plan = pool_plan(ctx, lite);
         if (plan.warps_per_block == 0) {
             ctx->err = "pooled kernel: the slot pool does not fit in shared memory";
             return NRRT_ERR_LIMIT;

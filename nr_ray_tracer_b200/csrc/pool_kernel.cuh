@@ -48,7 +48,12 @@ enum : uint32_t {
 // running sum, hit attributes, work-item bookkeeping) and the world-space ray an instance visit has to come back to —
 // live in global memory (L2-resident: a few tens of MB for the whole GPU), structure of arrays over all pool slots of
 // the launch.  Keeping them out of shared memory is what lets 16 warps x 64 slots fit on an SM instead of 9.
-template <uint32_t F, int NS>
+//
+// LITE (small scenes, where a closest-hit query is a handful of node visits): two stages only.  TRAVERSE runs the
+// lane-owned Traversal of rt_device.cuh to completion for up to 32 ray-ready slots, its working state in registers
+// and a per-lane stack; SHADE is the stage above.  A slot then carries only path state, and all of it — the "cold"
+// fields too — stays in shared memory (no L2 round trip where shading dominates).
+template <uint32_t F, int NS, bool LITE = false>
 struct Pool {
     static constexpr bool kInst = (F & NRRT_F_INSTANCES) != 0;
     static constexpr bool kUv = (F & NRRT_F_PLANES) && (F & NRRT_F_TEXTURED);
@@ -61,34 +66,49 @@ struct Pool {
     static constexpr int W_CUR = 1, W_TCULL = 2, W_R32 = 3 /* 7 */, W_BPRIM = 10;
     static constexpr int W_CINST = 11;                         // cur_inst: 4 x u16 in 2 words (kInst)
     static constexpr int W_STACK = W_CINST + (kInst ? 2 : 0);
-    // the traversal stack (cap entries, chosen per scene from nrrt_scene_desc.max_stack) comes last
-    __host__ __device__ static constexpr size_t bytes_per_warp(uint32_t cap) {
-        return (((size_t)NS * (8 * ND + 4 * (W_STACK + cap)) + 32 * 4) + 15) & ~(size_t)15;  // + assignment table
-    }
+    static constexpr int W_BPRIM_LITE = 1;                     // LITE: the slot's hot words are CTL and BPRIM only
+    static constexpr int NWH = LITE ? 2 : W_STACK;             // hot words before the per-slot stack (full) / cold words (LITE)
     // ---- cold doubles
     static constexpr int C_T = 0, C_SUM = 3, C_P = 6;
     static constexpr int C_AB = 9;                            // alpha, beta (kUv)
     static constexpr int C_DOBJ = C_AB + (kUv ? 2 : 0);       // object-space direction of the best hit (kInst)
-    static constexpr int C_WRAY = C_DOBJ + (kInst ? 3 : 0);   // world ray, saved while the slot is inside an instance (kInst)
-    static constexpr int C_TIME = C_WRAY + (kInst ? 6 : 0);   // Ray::time (kMotion)
+    static constexpr int C_WRAY = C_DOBJ + (kInst ? 3 : 0);   // world ray, saved while the slot is inside an instance (kInst, full)
+    static constexpr int C_TIME = C_WRAY + ((kInst && !LITE) ? 6 : 0);   // Ray::time (kMotion)
     static constexpr int NCD = C_TIME + (kMotion ? 1 : 0);
     // ---- cold words
     static constexpr int CW_ITEM = 0, CW_SAMPLE = 1, CW_BOUNCE = 2;
     static constexpr int CW_BINST = 3;                        // best.inst: 4 x u16 in 2 words (kInst)
     static constexpr int NCW = CW_BINST + (kInst ? 2 : 0);
-    __host__ __device__ static constexpr size_t cold_bytes_per_slot() { return 8 * NCD + 4 * NCW; }
+    __host__ __device__ static constexpr size_t cold_bytes_per_slot() { return LITE ? 0 : 8 * NCD + 4 * NCW; }
+    // Shared memory of one warp.  Full: slots x (hot doubles, hot words, stack of `cap` entries), assignment table.
+    // LITE: slots x (hot + cold doubles, hot + cold words), assignment table, and per LANE a stack of `cap` entries and
+    // the object-space ray of the instance being traversed.
+    static constexpr int kLaneDoubles = (LITE && kInst) ? 6 : 0;
+    static constexpr int kAssign = LITE ? ((NS + 31) & ~31) : 32;  // assignment table entries (LITE: every ray-ready slot)
+    __host__ __device__ static constexpr size_t bytes_per_warp(uint32_t cap) {
+        const size_t b = LITE ? (size_t)NS * (8 * (ND + NCD) + 4 * (NWH + NCW)) + 32 * (8 * kLaneDoubles + 4 * cap) + kAssign * 4
+                              : (size_t)NS * (8 * ND + 4 * (W_STACK + cap)) + kAssign * 4;
+        return (b + 15) & ~(size_t)15;
+    }
 
     double* D;
     uint32_t* W;
     uint32_t* assign;
+    double* lane_d;     // LITE: this lane's object-space ray, lane_d[k * 32]
+    uint32_t* lane_stack;  // LITE: this lane's traversal stack, lane_stack[k * 32]
     double* CD;       // cold doubles, already offset to this warp's first slot
     uint32_t* CW;     // cold words, likewise
     size_t cstride;   // pool slots in the launch
     uint32_t cap;     // traversal stack entries per slot
     __device__ __forceinline__ double& d(int k, uint32_t s) const { return D[k * NS + s]; }
     __device__ __forceinline__ uint32_t& w(int k, uint32_t s) const { return W[k * NS + s]; }
-    __device__ __forceinline__ double& cd(int k, uint32_t s) const { return CD[(size_t)k * cstride + s]; }
-    __device__ __forceinline__ uint32_t& cw(int k, uint32_t s) const { return CW[(size_t)k * cstride + s]; }
+    __device__ __forceinline__ double& cd(int k, uint32_t s) const {
+        return LITE ? D[(ND + k) * NS + s] : CD[(size_t)k * cstride + s];
+    }
+    __device__ __forceinline__ uint32_t& cw(int k, uint32_t s) const {
+        return LITE ? W[(NWH + k) * NS + s] : CW[(size_t)k * cstride + s];
+    }
+    __device__ __forceinline__ uint32_t& bprim(uint32_t s) const { return w(LITE ? W_BPRIM_LITE : W_BPRIM, s); }
     __device__ __forceinline__ d3 ld3d(int k, uint32_t s) const { return mk3(d(k, s), d(k + 1, s), d(k + 2, s)); }
     __device__ __forceinline__ void st3d(int k, uint32_t s, d3 v) const { d(k, s) = v.x, d(k + 1, s) = v.y, d(k + 2, s) = v.z; }
     __device__ __forceinline__ d3 ld3c(int k, uint32_t s) const { return mk3(cd(k, s), cd(k + 1, s), cd(k + 2, s)); }
@@ -151,16 +171,16 @@ __device__ __forceinline__ uint32_t classify_ref(uint32_t cur, bool screened = f
 }
 
 // ---- start of a closest-hit query (Traversal::begin on pool state): returns the first entry
-template <uint32_t F, int NS>
-__device__ __forceinline__ uint32_t pool_begin(const DevScene& S, const Pool<F, NS>& P, uint32_t s, d3 wo, d3 wd) {
-    using PL = Pool<F, NS>;
+template <uint32_t F, int NS, bool LITE>
+__device__ __forceinline__ uint32_t pool_begin(const DevScene& S, const Pool<F, NS, LITE>& P, uint32_t s, d3 wo, d3 wd) {
+    using PL = Pool<F, NS, LITE>;
     const double tmin = 0.001, tmax = NRRT_INF;
     const float tmin32 = (float)tmin, tmax32 = 3.4e38f;
     const Ray32 r32 = make_ray32(wo, wd);
     P.st_r32(s, r32);
     P.w(PL::W_TCULL, s) = __float_as_uint(3.4e38f);
     P.d(PL::D_BT, s) = NRRT_INF;
-    P.w(PL::W_BPRIM, s) = NRRT_REF_NONE;
+    P.bprim(s) = NRRT_REF_NONE;
     uint32_t cur = S.root;
     if (NRRT_REF_TYPE(cur) == NRRT_REF_NODE) {  // an inner node tests its own box (object.rs:102)
         if (!root_box_test<false>(&S.root_box, r32, wo, wd, tmin, tmax, tmin32, tmax32, nullptr)) cur = NRRT_REF_NONE;
@@ -177,10 +197,10 @@ __device__ __forceinline__ uint32_t pool_begin(const DevScene& S, const Pool<F, 
 // ---- NODE stage.  A lane walks inner nodes; when it lands on a plane leaf it runs the f32 reject-only test right
 // here (plane_prereject) and, if that proves a miss, takes the next stack entry and goes on — four out of five
 // primitive tests on a mesh end this way, without a visit to the PRIM stage.
-template <uint32_t F, int NS>
-__device__ __forceinline__ void pool_node(const DevScene& S, const Pool<F, NS>& P, uint32_t s, bool valid,
+template <uint32_t F, int NS, bool LITE>
+__device__ __forceinline__ void pool_node(const DevScene& S, const Pool<F, NS, LITE>& P, uint32_t s, bool valid,
                                           uint32_t n_take) {
-    using PL = Pool<F, NS>;
+    using PL = Pool<F, NS, LITE>;
     constexpr bool kPre = NRRT_POOL_PREREJECT == 1 && (F & NRRT_F_PLANES) != 0;
     const float tmin32 = 0.001f, tmax32 = 3.4e38f;
     uint32_t ctl = 0, cur = NRRT_REF_NONE, sp = 0;
@@ -252,9 +272,9 @@ __device__ __forceinline__ void pool_node(const DevScene& S, const Pool<F, NS>& 
 }
 
 // ---- PRIM stage: one exact primitive test, then the next stack entry
-template <uint32_t F, int NS>
-__device__ __forceinline__ void pool_prim(const DevScene& S, const Pool<F, NS>& P, uint32_t s, bool valid) {
-    using PL = Pool<F, NS>;
+template <uint32_t F, int NS, bool LITE>
+__device__ __forceinline__ void pool_prim(const DevScene& S, const Pool<F, NS, LITE>& P, uint32_t s, bool valid) {
+    using PL = Pool<F, NS, LITE>;
     if (!valid) return;
     const double tmin = 0.001, tmax = NRRT_INF;
     const uint32_t ctl = P.w(PL::W_CTL, s);
@@ -285,11 +305,11 @@ __device__ __forceinline__ void pool_prim(const DevScene& S, const Pool<F, NS>& 
             InstChain cc, bc;
             cc.clear(), bc.clear();
             if (PL::kInst) cc = P.ld_cur_chain(s), bc = P.ld_best_chain(s);
-            take = tie_candidate_wins(S, leaf, cc, level, bc, P.w(PL::W_BPRIM, s), bdepth);
+            take = tie_candidate_wins(S, leaf, cc, level, bc, P.bprim(s), bdepth);
         }
         if (take) {
             P.d(PL::D_BT, s) = t;
-            P.w(PL::W_BPRIM, s) = leaf;
+            P.bprim(s) = leaf;
             bdepth = level;
             if (PL::kInst && level) {
                 P.cw(PL::CW_BINST, s) = P.w(PL::W_CINST, s), P.cw(PL::CW_BINST + 1, s) = P.w(PL::W_CINST + 1, s);
@@ -308,9 +328,9 @@ __device__ __forceinline__ void pool_prim(const DevScene& S, const Pool<F, NS>& 
 }
 
 // ---- INST stage: enter a wrapper chain, or leave one (level marker)
-template <uint32_t F, int NS>
-__device__ __forceinline__ void pool_inst(const DevScene& S, const Pool<F, NS>& P, uint32_t s, bool valid) {
-    using PL = Pool<F, NS>;
+template <uint32_t F, int NS, bool LITE>
+__device__ __forceinline__ void pool_inst(const DevScene& S, const Pool<F, NS, LITE>& P, uint32_t s, bool valid) {
+    using PL = Pool<F, NS, LITE>;
     if (!PL::kInst || !valid) return;
     const double tmin = 0.001, tmax = NRRT_INF;
     const float tmin32 = 0.001f, tmax32 = 3.4e38f;
@@ -362,12 +382,78 @@ __device__ __forceinline__ void pool_inst(const DevScene& S, const Pool<F, NS>& 
     P.w(PL::W_CTL, s) = ctl_make(classify_ref<F>(cur), level, ctl_bdepth(ctl), sp);
 }
 
-// ---- SHADE stage: shade a finished query, account finished paths, next camera ray / work item, start the next query
+// ---- TRAVERSE stage (LITE): whole closest-hit queries, lane-owned traversal state
+// Per-query context of Traversal (rt_device.cuh): world ray from the slot, object-space ray in the lane's scratch,
+// attributes of a new best hit straight into the slot.
 template <uint32_t F, int NS>
+struct PoolLiteCtx {
+    static constexpr bool kRayInCtx = true;
+    using PL = Pool<F, NS, true>;
+    const PL& P;
+    uint32_t s;
+    __device__ __forceinline__ double time() const { return PL::kMotion ? P.cd(PL::C_TIME, s) : 0.0; }
+    __device__ __forceinline__ void get(d3& oo, d3& dd) const { P.ld_ray(s, oo, dd); }
+    __device__ __forceinline__ void get_obj(d3& oo, d3& dd) const {
+        const double* q = P.lane_d;
+        oo = mk3(q[0], q[32], q[64]), dd = mk3(q[96], q[128], q[160]);
+    }
+    __device__ __forceinline__ void put_obj(d3 oo, d3 dd) const {
+        double* q = P.lane_d;
+        q[0] = oo.x, q[32] = oo.y, q[64] = oo.z, q[96] = dd.x, q[128] = dd.y, q[160] = dd.z;
+    }
+    __device__ __forceinline__ void put(uint32_t level, d3 p, double a, double b, d3 dobj) const {
+        P.st3c(PL::C_P, s, p);
+        if (PL::kUv) P.cd(PL::C_AB, s) = a, P.cd(PL::C_AB + 1, s) = b;
+        if (PL::kInst && level) P.st3c(PL::C_DOBJ, s, dobj);
+    }
+};
+// WIDE: walk the four-slot nodes, or the binary ones (what the small scenes this variant serves are uploaded with too).
+// The assignment table holds ALL n_ready ray-ready slots of the pool (up to NS): the lanes start with the first 32 and,
+// whenever NRRT_POOL_REFILL_MIN of them have finished their query, the idle lanes take the next slots from the table
+// — queries differ in length (an instance entry, a deeper subtree), and without the refill the stage ran with 11 of
+// 32 lanes while it waited for the longest one.
+#ifndef NRRT_POOL_REFILL_MIN
+#define NRRT_POOL_REFILL_MIN 8
+#endif
+template <uint32_t F, int NS, bool WIDE>
+__device__ __forceinline__ void pool_traverse(const DevScene& S, const Pool<F, NS, true>& P, uint32_t n_ready) {
+    using PL = Pool<F, NS, true>;
+    const uint32_t lane = threadIdx.x & 31u;
+    Traversal<false, false, F, false, WIDE> tr;
+    uint32_t s = 0, next = 0;
+    bool running = false;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !running);
+        if (next < n_ready && (idle == 0xffffffffu || __popc(idle) >= NRRT_POOL_REFILL_MIN)) {
+            const uint32_t mine = next + __popc(idle & ((1u << lane) - 1u));
+            if (!running && mine < n_ready) {
+                s = P.assign[mine];
+                NRRT_CHECK(s < NS && ctl_state(P.w(PL::W_CTL, s)) == PS_NODE, "TRAVERSE: slot is not ray-ready");
+                tr.begin(S, PoolLiteCtx<F, NS>{P, s}, 0.001, NRRT_INF, nullptr);
+                running = true;
+            }
+            next += __popc(idle);
+        }
+        if (!__any_sync(0xffffffffu, running)) break;
+        if (tr.round(S, PoolLiteCtx<F, NS>{P, s}, 0.001, NRRT_INF, P.lane_stack, 32, nullptr, running) && running) {
+            P.d(PL::D_BT, s) = tr.best.t;
+            P.bprim(s) = tr.best.prim;
+            if (PL::kInst && tr.best.depth) {
+                P.cw(PL::CW_BINST, s) = tr.best.inst.a | (tr.best.inst.b << 16);
+                P.cw(PL::CW_BINST + 1, s) = tr.best.inst.c | (tr.best.inst.d << 16);
+            }
+            P.w(PL::W_CTL, s) = ctl_make(PS_HIT, 0, tr.best.depth, 0);
+            running = false;
+        }
+    }
+}
+
+// ---- SHADE stage: shade a finished query, account finished paths, next camera ray / work item, start the next query
+template <uint32_t F, int NS, bool LITE>
 __device__ __forceinline__ void pool_shade(const DevScene& S, const nrrt_camera& cam, const RenderParams& RP,
-                                           const Pool<F, NS>& P, uint32_t s, bool valid, double* __restrict__ partials,
+                                           const Pool<F, NS, LITE>& P, uint32_t s, bool valid, double* __restrict__ partials,
                                            unsigned long long* __restrict__ counters, uint32_t& segs, uint32_t& paths) {
-    using PL = Pool<F, NS>;
+    using PL = Pool<F, NS, LITE>;
     if (!valid) return;
     const uint32_t ctl = P.w(PL::W_CTL, s);
     uint32_t state = ctl_state(ctl);
@@ -389,7 +475,7 @@ __device__ __forceinline__ void pool_shade(const DevScene& S, const nrrt_camera&
         d3 L = mk3(0.0, 0.0, 0.0);
         bool alive;
         HitId h;
-        h.prim = P.w(PL::W_BPRIM, s);
+        h.prim = P.bprim(s);
         if (h.prim == NRRT_REF_NONE) {  // camera.rs:298
             L = mul3(T, ld3(cam.background));
             alive = false;
@@ -448,8 +534,12 @@ __device__ __forceinline__ void pool_shade(const DevScene& S, const nrrt_camera&
             start = true;
         }
         if (!start) break;
-        cur = pool_begin<F, NS>(S, P, s, o, d);
         ++segs;
+        if (LITE) {  // the TRAVERSE stage starts the query itself
+            state = PS_NODE;
+            break;
+        }
+        cur = pool_begin<F, NS, LITE>(S, P, s, o, d);
         state = classify_ref<F>(cur);
         // A camera ray that misses the scene's root box is a finished path on the spot (every other camera ray of an
         // object in front of a background): account for it here instead of spending another SHADE visit on it.
@@ -470,7 +560,7 @@ __device__ __forceinline__ void pool_shade(const DevScene& S, const nrrt_camera&
     P.cw(PL::CW_ITEM, s) = item;
     P.cw(PL::CW_SAMPLE, s) = smp.sample;
     P.cw(PL::CW_BOUNCE, s) = bounce;
-    P.w(PL::W_CUR, s) = cur;
+    if (!LITE) P.w(PL::W_CUR, s) = cur;
     P.w(PL::W_CTL, s) = ctl_make(state, 0, 0, 0);
 }
 
@@ -480,24 +570,32 @@ __device__ __forceinline__ void pool_shade(const DevScene& S, const nrrt_camera&
 #ifndef NRRT_POOL_MIN_BLOCKS
 #define NRRT_POOL_MIN_BLOCKS 4  // resident blocks per SM the kernel is compiled for (register budget 65536 / (MB * 128))
 #endif
-template <uint32_t F, int NS>
+template <uint32_t F, int NS, bool LITE>
 __global__ void __launch_bounds__(NRRT_POOL_WARPS * 32, NRRT_POOL_MIN_BLOCKS)
 k_render_pool(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_camera cam,
               const __grid_constant__ RenderParams RP, double* __restrict__ partials,
               unsigned long long* __restrict__ counters, uint32_t stack_cap, double* __restrict__ cold,
               uint32_t cold_slots) {
-    using PL = Pool<F, NS>;
+    using PL = Pool<F, NS, LITE>;
     extern __shared__ __align__(16) unsigned char s_pool[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     unsigned char* base = s_pool + (size_t)warp * PL::bytes_per_warp(stack_cap);
     PL P;
     P.D = reinterpret_cast<double*>(base);
-    P.W = reinterpret_cast<uint32_t*>(base + (size_t)NS * 8 * PL::ND);
-    P.assign = P.W + (size_t)NS * (PL::W_STACK + stack_cap);
+    if (LITE) {  // doubles: slots x (hot + cold), lanes x object-space ray; words: slots x (hot + cold), assignment, lane stacks
+        P.lane_d = P.D + (size_t)NS * (PL::ND + PL::NCD) + lane;
+        P.W = reinterpret_cast<uint32_t*>(P.D + (size_t)NS * (PL::ND + PL::NCD) + 32 * PL::kLaneDoubles);
+        P.assign = P.W + (size_t)NS * (PL::NWH + PL::NCW);
+        P.lane_stack = P.assign + PL::kAssign + lane;
+    } else {
+        P.lane_d = nullptr, P.lane_stack = nullptr;
+        P.W = reinterpret_cast<uint32_t*>(base + (size_t)NS * 8 * PL::ND);
+        P.assign = P.W + (size_t)NS * (PL::W_STACK + stack_cap);
+    }
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
     P.cstride = cold_slots;
     P.cap = stack_cap;
-    NRRT_CHECK((size_t)(gwarp + 1) * NS <= cold_slots, "cold state index");
+    NRRT_CHECK(LITE || (size_t)(gwarp + 1) * NS <= cold_slots, "cold state index");
     P.CD = cold + (size_t)gwarp * NS;
     P.CW = reinterpret_cast<uint32_t*>(cold + (size_t)PL::NCD * cold_slots) + (size_t)gwarp * NS;
     uint32_t segs = 0, paths = 0;
@@ -507,7 +605,7 @@ k_render_pool(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
         P.cw(PL::CW_ITEM, s) = item;
         P.cw(PL::CW_SAMPLE, s) = 0;
         P.cw(PL::CW_BOUNCE, s) = 0;
-        P.w(PL::W_CUR, s) = NRRT_REF_NONE;
+        if (!LITE) P.w(PL::W_CUR, s) = NRRT_REF_NONE;
         P.w(PL::W_CTL, s) = ctl_make(item < RP.n_slots ? PS_NEED_ITEM : PS_RETIRED, 0, 0, 0);
     }
     constexpr int NSET = (NS + 31) / 32;  // slots a lane inspects when scheduling
@@ -530,6 +628,12 @@ k_render_pool(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
         if (cnt[2] > best) phase = 2, best = cnt[2];
         if (cnt[1] > best) phase = 1, best = cnt[1];
         if (cnt[0] > best) phase = 0, best = cnt[0];
+        if (LITE) {
+            // two stages: drain SHADE completely, then TRAVERSE finds EVERY live slot ray-ready and works through them
+            // 32 at a time with in-stage refill — the long queries of one batch overlap the short ones of the next
+            phase = cnt[3] ? 3u : 0u;
+            best = cnt[3] ? cnt[3] : cnt[0];
+        }
         // ---- hand the first min(32, best) ready slots to the lanes
         uint32_t rank = 0;
 #pragma unroll
@@ -537,7 +641,7 @@ k_render_pool(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
             const bool mine = phase == 3 ? st[j] >= PS_HIT : st[j] == phase + 1;
             const unsigned m = __ballot_sync(0xffffffffu, mine);
             const uint32_t r = rank + __popc(m & ((1u << lane) - 1u));
-            if (mine && r < 32) P.assign[r] = lane + 32 * j;
+            if (mine && r < (uint32_t)((LITE && phase == 0) ? PL::kAssign : 32)) P.assign[r] = lane + 32 * j;
             rank += __popc(m);
         }
         __syncwarp();
@@ -548,10 +652,17 @@ k_render_pool(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
         NRRT_CHECK(!valid || (phase == 3 ? ctl_state(P.w(PL::W_CTL, s)) >= PS_HIT : ctl_state(P.w(PL::W_CTL, s)) == phase + 1),
                    "slot handed to the wrong stage");
         __syncwarp();
-        if (phase == 0) pool_node<F, NS>(S, P, s, valid, n_take);
-        else if (phase == 1) pool_prim<F, NS>(S, P, s, valid);
-        else if (phase == 2) pool_inst<F, NS>(S, P, s, valid);
-        else pool_shade<F, NS>(S, cam, RP, P, s, valid, partials, counters, segs, paths);
+        if (LITE) {
+            if constexpr (LITE) {
+                if (phase == 0) pool_traverse<F, NS, false>(S, P, best);
+                else pool_shade<F, NS, true>(S, cam, RP, P, s, valid, partials, counters, segs, paths);
+            }
+        } else if constexpr (!LITE) {
+            if (phase == 0) pool_node<F, NS, false>(S, P, s, valid, n_take);
+            else if (phase == 1) pool_prim<F, NS, false>(S, P, s, valid);
+            else if (phase == 2) pool_inst<F, NS, false>(S, P, s, valid);
+            else pool_shade<F, NS, false>(S, cam, RP, P, s, valid, partials, counters, segs, paths);
+        }
     }
     // block-level reduction of the counters
     __shared__ unsigned long long s_cnt[2];

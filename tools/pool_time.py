@@ -11,7 +11,7 @@ M = {"auto": A.MODE_AUTO, "pool": A.MODE_POOL, "fused": A.MODE_FUSED, "wavefront
 ctx = api.Context(0)
 out = []
 for name, spp in (("utah-teapot-scene.json", 64), ("cornell-teapot-scene.json", 32), ("cornell-box-scene.json", 64),
-                  ("spheres.toml", 32), ("noise.toml", 32)):
+                  ("spheres.toml", 32), ("noise.toml", 32), ("earth.toml", 64)):
     g = load_scene("scenes/" + name, camera_override=CameraConfig(width=1920, height=1080, samples_per_pixel=spp, ray_max_bounces=50))
     hs = api.HostScene(g, bvh=os.environ.get("BVH", "reference"))
     ctx.upload(hs)

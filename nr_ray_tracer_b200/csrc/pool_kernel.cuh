@@ -28,6 +28,18 @@
                                    // 3720, 1/2 2091 / 1949 / 3786.  Slots per warp: 48 1665, 56 1946, 64 2031, 80 1860.
 #endif
 #define NRRT_POOL_TRIVIAL_MAX 4     // camera rays that miss the scene's root box, absorbed per SHADE visit
+#ifndef NRRT_POOL_W_SHADE
+#define NRRT_POOL_W_SHADE 8  // stage weights (x/8) of the scheduler's "most ready slots" rule
+#endif
+#ifndef NRRT_POOL_W_INST
+#define NRRT_POOL_W_INST 8
+#endif
+#ifndef NRRT_POOL_W_PRIM
+#define NRRT_POOL_W_PRIM 8
+#endif
+#ifndef NRRT_POOL_W_NODE
+#define NRRT_POOL_W_NODE 8
+#endif
 #ifndef NRRT_POOL_SCREEN_MIN
 #define NRRT_POOL_SCREEN_MIN 8      // NODE stage: lanes holding a plane leaf before the reject-only test runs for them
 #endif
@@ -624,10 +636,12 @@ k_render_pool(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
         const uint32_t cnt[4] = {packed & 255u, (packed >> 8) & 255u, (packed >> 16) & 255u, packed >> 24};  // NODE PRIM INST SHADE
         if (packed == 0) break;
         // the stage with the most ready slots (ties: later stages first — they free slots for new rays)
-        uint32_t phase = 3, best = cnt[3];
-        if (cnt[2] > best) phase = 2, best = cnt[2];
-        if (cnt[1] > best) phase = 1, best = cnt[1];
-        if (cnt[0] > best) phase = 0, best = cnt[0];
+        // (a stage's count is weighed by NRRT_POOL_W_* / 8 before the comparison: a long stage is worth running only
+        // with more lanes; a stage with nothing ready never wins)
+        uint32_t phase = 3, best = cnt[3], score = cnt[3] * NRRT_POOL_W_SHADE;
+        if (cnt[2] * NRRT_POOL_W_INST > score) phase = 2, best = cnt[2], score = cnt[2] * NRRT_POOL_W_INST;
+        if (cnt[1] * NRRT_POOL_W_PRIM > score) phase = 1, best = cnt[1], score = cnt[1] * NRRT_POOL_W_PRIM;
+        if (cnt[0] * NRRT_POOL_W_NODE > score) phase = 0, best = cnt[0], score = cnt[0] * NRRT_POOL_W_NODE;
         if (LITE) {
             // two stages: drain SHADE completely, then TRAVERSE finds EVERY live slot ray-ready and works through them
             // 32 at a time with in-stage refill — the long queries of one batch overlap the short ones of the next

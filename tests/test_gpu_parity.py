@@ -683,3 +683,24 @@ def test_progress_is_reported_while_a_single_launch_render_runs(gpu_ctx):
         assert done == sorted(done) and len(set(done)) == len(done)
         assert len(calls) >= 3, calls          # at least two intermediate reports in a ~0.15 s render
     del hs
+
+
+def test_checked_build_runs_clean(tmp_path):
+    """The stand-in for compute-sanitizer (closed on the GPU pool): a library built with -DNRRT_CHECKED=1 bounds-checks
+    every traversal-stack push, slot index and scene index on the device and traps on a violation.  All kernel designs
+    on the Cornell box, the pooled and fused kernels on the teapot mesh, the sphere field and a noise scene, plus a
+    fixed-ray batch each, must run through it (tools/sanitize_run.py, in a process of its own so a trap cannot take the
+    test session's CUDA context with it)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "build", "lib_checked.so")
+    srcs = [os.path.join(root, "nr_ray_tracer_b200", "csrc", f) for f in ("nrrt_device.cu", "rt_device.cuh", "pool_kernel.cuh")]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(f) for f in srcs):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "build_variant.py"), "checked", "-DNRRT_CHECKED=1"],
+                           capture_output=True, text=True, cwd=root)
+        assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_run.py")], capture_output=True, text=True,
+                       cwd=root, env=dict(os.environ, NRRT_B200_LIB=lib), timeout=600)
+    assert r.returncode == 0 and "sanitize_run done" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "NRRT_CHECK failed" not in r.stdout + r.stderr

@@ -9,7 +9,8 @@ from nr_ray_tracer_b200.scene_config import CameraConfig, load_scene  # noqa: E4
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cornell-box-scene.json"
 spp = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-mode = {"mega": A.MODE_MEGAKERNEL, "wavefront": A.MODE_WAVEFRONT, "pool": A.MODE_POOL}.get(sys.argv[3] if len(sys.argv) > 3 else "", A.MODE_FUSED)
+mode = {"mega": A.MODE_MEGAKERNEL, "wavefront": A.MODE_WAVEFRONT, "pool": A.MODE_POOL, "fused": A.MODE_FUSED,
+        "auto": A.MODE_AUTO}[sys.argv[3] if len(sys.argv) > 3 else "auto"]
 ctx = api.Context(0)
 g = load_scene("scenes/" + name, camera_override=CameraConfig(width=1920, height=1080, samples_per_pixel=spp,
                                                               ray_max_bounces=50))

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""Runs the five BASELINE.json configs on one GPU (wavefront kernels) next to a bounded CPU sample of the
-oracle, plus a traversal-only microbenchmark (coherent primary rays through nrrt_trace_rays) per scene.
+"""Runs the five BASELINE.json configs on one GPU (product path: NRRT_MODE_AUTO) next to a bounded CPU sample of the
+oracle, plus the traversal-only microbenchmark bench.py uses as the ceiling (>= 2 M coherent primary rays through
+nrrt_trace_rays, NRRT_TRACE_COMPACT: closest hit only, 16 B out per ray) per scene.
 Writes gpurun_out/configs.json and prints a markdown table.  Usage: run_configs.py [--quick]"""
 import json
 import os
@@ -26,14 +27,8 @@ CONFIGS = [
 ]
 
 
-def primary_rays(cam):
-    W, H = cam.width, cam.height
-    xs, ys = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
-    tl, du, dv = (np.array(list(v)) for v in (cam.viewport_top_left, cam.pixel_delta_u, cam.pixel_delta_v))
-    o = np.array(list(cam.look_from))
-    pts = tl + xs[..., None] * du + ys[..., None] * dv
-    rays = np.concatenate([np.broadcast_to(o, pts.shape), pts - o], axis=-1).reshape(-1, 6)
-    return np.ascontiguousarray(rays)
+sys.path.insert(0, ROOT)
+from bench import primary_rays  # noqa: E402  (the same ray set bench.py traces)
 
 
 def main():
@@ -48,17 +43,18 @@ def main():
         ctx.upload(host)
         cam = api.camera_build(g.camera.to_builder_config())
         fb = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
-        ctx.render(cam, seed=0, out_device_ptr=fb.data_ptr(), max_slots=1 << 18)  # warm-up (small)
+        ctx.render(cam, seed=0, out_device_ptr=fb.data_ptr(), max_slots=1 << 14)  # warm-up (small)
         t0 = time.perf_counter()
         _, st = ctx.render(cam, seed=0, out_device_ptr=fb.data_ptr())
         wall = time.perf_counter() - t0
         # traversal-only microbenchmark: coherent primary rays, no shading
         rays = torch.from_numpy(primary_rays(cam)).cuda()
-        hits = torch.zeros((rays.shape[0], 112), dtype=torch.uint8, device="cuda")
+        hits = torch.zeros((rays.shape[0], 16), dtype=torch.uint8, device="cuda")
         best = 0.0
-        for _ in range(3):
-            ts = ctx.trace_rays_device(rays.data_ptr(), rays.shape[0], hits.data_ptr())
+        for _ in range(6):
+            ts = ctx.trace_rays_device(rays.data_ptr(), rays.shape[0], hits.data_ptr(), compact=True)
             best = max(best, rays.shape[0] / ts["kernel_ms"] / 1e3)
+        n_micro = rays.shape[0]
         del rays, hits
         # CPU sample
         gc = load_scene(scene, camera_override=CameraConfig(width=W, height=H, samples_per_pixel=cpu_spp, ray_max_bounces=depth))
@@ -69,8 +65,9 @@ def main():
         row = {"config": name, "scene": scene, "width": W, "height": H, "spp": gpu_spp, "depth": cam.ray_max_bounces,
                "paths": st["paths"], "segments": st["segments"], "segments_per_path": st["segments"] / st["paths"],
                "gpu_mrays_s": st["segments"] / st["device_ms"] / 1e3, "gpu_time_to_image_s": st["device_ms"] / 1e3,
-               "gpu_wall_s": wall, "launches": st["launches"],
-               "primary_ray_traversal_mrays_s": best,
+               "gpu_wall_s": wall, "launches": st["launches"], "kernel_design": A.MODE_NAMES[st["mode"]],
+               "primary_ray_traversal_mrays_s": best, "microbench_rays": int(n_micro),
+               "frac_of_traversal_microbench": (st["segments"] / st["device_ms"] / 1e3) / best,
                "cpu_mrays_s": cnt["segments"] / cpu_dt / 1e6, "cpu_cores": len(os.sched_getaffinity(0)), "cpu_sample_spp": cpu_spp,
                "cpu_time_to_image_s_extrapolated": cpu_dt * gpu_spp / cpu_spp,
                "prims": g.count_primitives(), "nodes": host.desc.n_nodes, "instances": host.desc.n_instances}
@@ -79,11 +76,11 @@ def main():
         print(json.dumps(row), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
-    print("\n| config | scene | size | spp | seg/path | GPU Mrays/s | GPU time-to-image | primary-ray traversal Mrays/s | CPU Mrays/s (cores) | CPU time-to-image (extrap.) | speed-up |")
-    print("|---|---|---|---|---|---|---|---|---|---|---|")
+    print("\n| config | scene | size | spp | kernel | seg/path | GPU Mrays/s | GPU time-to-image | traversal microbench Mrays/s | fraction | CPU Mrays/s (cores) | CPU time-to-image (extrap.) | speed-up |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     for r in out:
-        print(f"| {r['config']} | {os.path.basename(r['scene'])} | {r['width']}x{r['height']} | {r['spp']} | {r['segments_per_path']:.2f} | "
-              f"{r['gpu_mrays_s']:.0f} | {r['gpu_time_to_image_s']:.2f} s | {r['primary_ray_traversal_mrays_s']:.0f} | "
+        print(f"| {r['config']} | {os.path.basename(r['scene'])} | {r['width']}x{r['height']} | {r['spp']} | {r['kernel_design']} | {r['segments_per_path']:.2f} | "
+              f"{r['gpu_mrays_s']:.0f} | {r['gpu_time_to_image_s']:.2f} s | {r['primary_ray_traversal_mrays_s']:.0f} | {r['frac_of_traversal_microbench']:.2f} | "
               f"{r['cpu_mrays_s']:.1f} ({r['cpu_cores']}) | {r['cpu_time_to_image_s_extrapolated']:.0f} s | {r['speedup_vs_cpu']:.0f}x |")
 
 

@@ -22,5 +22,5 @@ if os.environ.get("WARMUP", "1") != "0":   # the first launch pays module loadin
         width=64, height=36, samples_per_pixel=1, ray_max_bounces=50)).camera.to_builder_config())
     ctx.render(warm, seed=1, mode=mode)
 img, st = ctx.render(cam, seed=1, mode=mode)
-print(f"{name} spp={spp}: {st['segments']/st['device_ms']/1e3:.1f} Mseg/s device_ms={st['device_ms']:.1f} "
+print(f"{name} spp={spp}: {st['segments']/st['device_ms']/1e3:.1f} Mseg/s segments={st['segments']} device_ms={st['device_ms']:.1f} "
       f"launches={st['launches']} mean={img.mean():.6f}")

@@ -70,8 +70,9 @@ struct FastDiv {
 struct RenderParams {
     uint2 key;               // Philox key
     uint32_t n_owned_pixels; // pixels rendered by this context
-    uint32_t chunk;          // samples per work item
-    uint32_t n_chunks;       // ceil(spp / chunk)
+    uint32_t chunk;          // samples of an equal-size work item (the first n_eq chunks of a pixel)
+    uint32_t n_eq;           // equal chunks; they cover samples [0, n_eq * chunk)
+    uint32_t n_chunks;       // work items per pixel = n_eq + the halving chunks over the remaining samples
     uint32_t n_items;        // n_owned_pixels * n_chunks
     uint32_t n_slots;        // paths in flight
     uint32_t rank, world, rows_per_block;
@@ -97,9 +98,16 @@ __device__ __forceinline__ uint32_t decode_item(const nrrt_camera& cam, const Re
                                                 WorkItem& wi) {
     uint32_t c = P.div_pixels.div(item), po = item - c * P.n_owned_pixels;
     owned_pixel(cam, P, po, wi.x, wi.y);
-    uint32_t first = c * P.chunk;
-    wi.sample_end = min(first + P.chunk, cam.samples_per_pixel);
-    return first;
+    const uint32_t spp = cam.samples_per_pixel;
+    if (c < P.n_eq) {
+        wi.sample_end = (c + 1) * P.chunk;
+        return c * P.chunk;
+    }
+    // the tail of the pixel halves: with R samples left after the equal chunks, tail chunk k covers
+    // [base + R - (R >> k), base + R - (R >> (k + 1))), the last one up to spp
+    const uint32_t base = P.n_eq * P.chunk, R = spp - base, k = c - P.n_eq;
+    wi.sample_end = (c + 1 == P.n_chunks) ? spp : base + R - (R >> (k + 1));
+    return base + R - (R >> k);
 }
 
 // COMPACT: the closest-hit query alone — 16 bytes out per ray, no HitRecord (traversal microbenchmark)
@@ -309,6 +317,10 @@ __global__ void k_encode_rgb8(const float* __restrict__ rgb, size_t n, float gam
 // attributes, object-space ray, time: 27 doubles per thread), so neither rays nor hit records ever round-trip
 // through HBM and there is no queue, no compaction and a single launch.  Traversal and shading use the same device functions as the
 // wavefront kernels and the same (pixel, sample-chunk) work items, so the image is bit-identical.
+#define NRRT_NO_ITEM 0xFFFFFFFFu
+#ifndef NRRT_ITEM_BLOCK
+#define NRRT_ITEM_BLOCK 128  // work items a warp takes from the global counter at a time
+#endif
 #ifndef NRRT_FUSED_MIN
 #define NRRT_FUSED_MIN 24  // lanes of a warp that must be waiting before a shading round runs.  Measured on B200, round 2
                            // (Cornell / spheres / noise / earth, Mrays/s; profiles/r02_fused_quorum_sweep.log): 16 6173 / 4558 /
@@ -374,6 +386,7 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
     Sampler smp{P.key, 0u, 0u};
     uint32_t bounce = 0;
     Traversal<false, false, F, SPEC, SPEC> tr;  // deep trees: four-slot nodes + speculation; small ones: binary nodes
+    uint32_t wb_next = 0, wb_end = 0;  // this warp's block of work items (warp-uniform)
 
     for (;;) {
         // ---- shading / regeneration round, voted by the warp
@@ -414,12 +427,32 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
                     if (smp.sample >= s_end) {  // item finished: publish, fetch the next one
                         size_t pb = (size_t)s_item * 3;
                         partials[pb] = sum.x, partials[pb + 1] = sum.y, partials[pb + 2] = sum.z;
-                        s_item = (uint32_t)atomicAdd(&counters[5], 1ull);
+                        s_item = NRRT_NO_ITEM;  // fetched below, by the warp
                         state = NEED_ITEM;
                     } else {
                         st[9 * NRRT_BLOCK] = sum.x, st[10 * NRRT_BLOCK] = sum.y, st[11 * NRRT_BLOCK] = sum.z;
                         state = NEED_PATH;
                     }
+                }
+            }
+            // Work items come to a WARP in blocks of NRRT_ITEM_BLOCK consecutive ones (= consecutive pixels of one chunk)
+            // and its lanes take them from there, so however far the lanes drift apart in time they stay on
+            // neighbouring pixels: same materials, same textures, same part of the tree.  One atomic per block.
+            {
+                const bool want = state == NEED_ITEM && s_item == NRRT_NO_ITEM;
+                const unsigned need = __ballot_sync(0xffffffffu, want);
+                if (need) {
+                    const uint32_t lane = threadIdx.x & 31u, n = __popc(need), rank = __popc(need & ((1u << lane) - 1u));
+                    const uint32_t avail = wb_end - wb_next;
+                    uint32_t fresh_base = 0;
+                    if (n > avail) {
+                        const uint32_t leader = __ffs(need) - 1;
+                        if (lane == leader) fresh_base = (uint32_t)atomicAdd(&counters[5], (unsigned long long)NRRT_ITEM_BLOCK);
+                        fresh_base = __shfl_sync(0xffffffffu, fresh_base, leader);
+                    }
+                    if (want) s_item = rank < avail ? wb_next + rank : fresh_base + (rank - avail);
+                    if (n > avail) wb_next = fresh_base + (n - avail), wb_end = fresh_base + NRRT_ITEM_BLOCK;
+                    else wb_next += n;
                 }
             }
             if (state == NEED_ITEM) {
@@ -463,7 +496,7 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
                     if (smp.sample >= s_end) {  // item finished: publish; the next shading round fetches another
                         size_t pb = (size_t)s_item * 3;
                         partials[pb] = sum.x, partials[pb + 1] = sum.y, partials[pb + 2] = sum.z;
-                        s_item = (uint32_t)atomicAdd(&counters[5], 1ull);
+                        s_item = NRRT_NO_ITEM;  // the next shading round fetches one
                         state = NEED_ITEM;
                         break;
                     }
@@ -1537,20 +1570,36 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     P.key = make_uint2((uint32_t)o.seed, (uint32_t)(o.seed >> 32));
     P.rank = o.rank, P.world = o.world, P.rows_per_block = o.rows_per_block;
     P.n_owned_pixels = owned_rows(H, o.rank, o.world, o.rows_per_block) * W;
-    // Work-item size.  It fixes the order in which a pixel's samples are summed, so it may depend only on what every
-    // rank of every partition agrees on — spp and the size of the WHOLE image — never on slots, rank or world: the
-    // image is then bit-identical for every slot count and GPU count.  An item should be a small fraction (1/16) of
-    // what one path slot gets to do in the whole render, so the tail of the render stays short, but no smaller: each
-    // item costs 24 bytes of scratch that k_resolve reads back.  Sized for up to 16 GPUs x 160 k resident slots; never
-    // more than 32 items per pixel.  (1080p x 1024 spp: 20 items of 52 samples; 4K x 4096 spp: 5 items — 1 GB of
-    // scratch where a fixed 32 needed 6.4 GB.)
-    {
-        const uint64_t spp = c.samples_per_pixel;
-        const uint64_t per_slot = total_pixels * spp / 2560000ull;  // samples one slot traces when 16 GPUs share the image
-        uint64_t chunk = std::max<uint64_t>(per_slot / 16, (spp + 31) / 32);
-        chunk = std::min<uint64_t>(std::max<uint64_t>(chunk, 1), spp);
-        P.chunk = (uint32_t)chunk;
-        P.n_chunks = (uint32_t)((spp + chunk - 1) / chunk);
+    // Work items of a pixel.  They fix the order in which its samples are summed, so they may depend only on what
+    // every rank of every partition agrees on — spp and the size of the WHOLE image — never on slots, rank or world:
+    // the image is then bit-identical for every slot count and GPU count.  Items are numbered chunk-major (every
+    // pixel's chunk 0, then every pixel's chunk 1, ...) and handed to a WARP in blocks of NRRT_ITEM_BLOCK consecutive
+    // ones, i.e. consecutive pixels of one chunk (see the kernels).  Measured (profiles/r02_chunk_schedules.log,
+    // r02_item_blocks_and_chunk_schedules.log):
+    //  * what matters most is that the lanes of a warp stay on neighbouring pixels — same materials, textures and
+    //    subtrees.  With one global counter and an item per lane that only held for tiny items (noise.toml: 5552
+    //    Mrays/s with 1-sample items, 4798 with 2-sample ones, 4361 with seven halving chunks); with per-warp blocks it
+    //    holds for any item size, and every scene gained 6-16 % (Cornell 6242 -> 6640, noise 4840 -> 5622, earth 11602
+    //    -> 12850, teapot 2094 -> 2211 at test sizes; 6482 -> 7006 and 2101 -> 2304 at the benchmark sizes);
+    //  * the render ENDS waiting for the last slots to finish their item, which is what eight GPUs sharing one image
+    //    lose to; so the last 1/16 of a pixel's samples goes in up to four HALVING chunks;
+    //  * each item costs 24 B of scratch: up to 16 equal chunks for images up to 3.7 Mpixel, 8 at 4K (1080p x 1024
+    //    spp: 15 x 60, then 62, 31, 16, 15; 4K x 4096 spp: 12 items per pixel, 2.4 GB where round 1 needed 6.4 GB).
+    {   // closed form, so the kernels need no table
+        const uint32_t spp = c.samples_per_pixel;
+        uint32_t eq_parts = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(8, 60000000ull / std::max<uint64_t>(total_pixels, 1)));
+        uint32_t tail_shift = 4, tail_max = 4;  // the last 1/16 of the samples in up to four halving chunks
+        if (const char* e = std::getenv("NRRT_CHUNKS")) std::sscanf(e, "%u,%u,%u", &eq_parts, &tail_shift, &tail_max);  // developer override
+        uint32_t R = tail_max ? (spp >> tail_shift) : 0;   // samples left to the halving tail
+        if (eq_parts == 0) R = spp;
+        const uint32_t head = spp - R;
+        P.chunk = eq_parts ? std::max<uint32_t>(1, (head + eq_parts - 1) / eq_parts) : 1;
+        P.n_eq = eq_parts ? head / P.chunk : 0;            // whole equal chunks; what they leave over joins the tail
+        R = spp - P.n_eq * P.chunk;
+        uint32_t n_tail = R ? 1 : 0;
+        while (n_tail && n_tail < std::max<uint32_t>(tail_max, 1) && (R >> n_tail) >= 1) ++n_tail;
+        P.n_chunks = P.n_eq + n_tail;
+        if (P.n_chunks == 0) P.n_chunks = 1, P.n_eq = 0;   // spp >= 1 always gives at least one chunk; belt and braces
     }
     const uint64_t n_items64 = (uint64_t)P.n_owned_pixels * P.n_chunks;
     if (n_items64 > 0xFFFFFFF0ull) {

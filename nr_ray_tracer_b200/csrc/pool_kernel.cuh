@@ -464,21 +464,22 @@ __device__ __forceinline__ void pool_traverse(const DevScene& S, const Pool<F, N
 template <uint32_t F, int NS, bool LITE>
 __device__ __forceinline__ void pool_shade(const DevScene& S, const nrrt_camera& cam, const RenderParams& RP,
                                            const Pool<F, NS, LITE>& P, uint32_t s, bool valid, double* __restrict__ partials,
-                                           unsigned long long* __restrict__ counters, uint32_t& segs, uint32_t& paths) {
+                                           unsigned long long* __restrict__ counters, uint32_t& segs, uint32_t& paths,
+                                           uint32_t& wb_next, uint32_t& wb_end) {
     using PL = Pool<F, NS, LITE>;
-    if (!valid) return;
-    const uint32_t ctl = P.w(PL::W_CTL, s);
+    // (called by all 32 lanes: the work-item fetch in the middle is a warp operation; lanes without a slot skip the rest)
+    const uint32_t ctl = valid ? P.w(PL::W_CTL, s) : ctl_make(PS_RETIRED, 0, 0, 0);
     uint32_t state = ctl_state(ctl);
-    uint32_t item = P.cw(PL::CW_ITEM, s);
+    uint32_t item = valid ? P.cw(PL::CW_ITEM, s) : 0u;
     WorkItem wi;
     wi.x = wi.y = wi.sample_end = 0;
     Sampler smp{RP.key, 0u, 0u};
-    if (state != PS_NEED_ITEM) {
+    if (valid && state != PS_NEED_ITEM) {
         decode_item(cam, RP, item, wi);
         smp.pixel = wi.y * cam.width + wi.x;
         smp.sample = P.cw(PL::CW_SAMPLE, s);
     }
-    uint32_t bounce = P.cw(PL::CW_BOUNCE, s);
+    uint32_t bounce = valid ? P.cw(PL::CW_BOUNCE, s) : 0u;
     d3 o = mk3(0, 0, 0), d = o;
     bool start = false;  // a new closest-hit query starts from (o, d)
     if (state == PS_HIT) {
@@ -515,7 +516,7 @@ __device__ __forceinline__ void pool_shade(const DevScene& S, const nrrt_camera&
             if (smp.sample >= wi.sample_end) {  // item finished: publish, fetch the next one
                 const size_t pb = (size_t)item * 3;
                 partials[pb] = sum.x, partials[pb + 1] = sum.y, partials[pb + 2] = sum.z;
-                item = (uint32_t)atomicAdd(&counters[5], 1ull);
+                item = NRRT_NO_ITEM;  // fetched below, by the warp
                 state = PS_NEED_ITEM;
             } else {
                 P.st3c(PL::C_SUM, s, sum);
@@ -523,6 +524,26 @@ __device__ __forceinline__ void pool_shade(const DevScene& S, const nrrt_camera&
             }
         }
     }
+    // Work items come to the WARP in blocks of NRRT_ITEM_BLOCK consecutive ones (= consecutive pixels of one chunk), so
+    // the slots of a pool stay on neighbouring pixels however far they drift apart in time; one atomic per block.
+    {
+        const bool want = state == PS_NEED_ITEM && item == NRRT_NO_ITEM;
+        const unsigned need = __ballot_sync(0xffffffffu, want);
+        if (need) {
+            const uint32_t lane = threadIdx.x & 31u, n = __popc(need), rank = __popc(need & ((1u << lane) - 1u));
+            const uint32_t avail = wb_end - wb_next;
+            uint32_t fresh_base = 0;
+            if (n > avail) {
+                const uint32_t leader = __ffs(need) - 1;
+                if (lane == leader) fresh_base = (uint32_t)atomicAdd(&counters[5], (unsigned long long)NRRT_ITEM_BLOCK);
+                fresh_base = __shfl_sync(0xffffffffu, fresh_base, leader);
+            }
+            if (want) item = rank < avail ? wb_next + rank : fresh_base + (rank - avail);
+            if (n > avail) wb_next = fresh_base + (n - avail), wb_end = fresh_base + NRRT_ITEM_BLOCK;
+            else wb_next += n;
+        }
+    }
+    if (!valid) return;
     if (state == PS_NEED_ITEM) {
         if (item >= RP.n_items) {
             P.cw(PL::CW_ITEM, s) = item;
@@ -562,8 +583,8 @@ __device__ __forceinline__ void pool_shade(const DevScene& S, const nrrt_camera&
         if (smp.sample >= wi.sample_end) {
             const size_t pb = (size_t)item * 3;
             partials[pb] = sum.x, partials[pb + 1] = sum.y, partials[pb + 2] = sum.z;
-            item = (uint32_t)atomicAdd(&counters[5], 1ull);
-            state = PS_NEED_ITEM;  // the next SHADE visit decodes it
+            item = NRRT_NO_ITEM;
+            state = PS_NEED_ITEM;  // the next SHADE visit fetches and decodes one
             break;
         }
         P.st3c(PL::C_SUM, s, sum);
@@ -611,6 +632,7 @@ k_render_pool(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
     P.CD = cold + (size_t)gwarp * NS;
     P.CW = reinterpret_cast<uint32_t*>(cold + (size_t)PL::NCD * cold_slots) + (size_t)gwarp * NS;
     uint32_t segs = 0, paths = 0;
+    uint32_t wb_next = 0, wb_end = 0;  // this warp's block of work items (warp-uniform)
     // the first n_slots items are pre-assigned (slot k of the grid takes item k); the counter starts at n_slots
     for (uint32_t s = lane; s < NS; s += 32) {
         const uint32_t item = gwarp * NS + s;
@@ -669,13 +691,13 @@ k_render_pool(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_c
         if (LITE) {
             if constexpr (LITE) {
                 if (phase == 0) pool_traverse<F, NS, false>(S, P, best);
-                else pool_shade<F, NS, true>(S, cam, RP, P, s, valid, partials, counters, segs, paths);
+                else pool_shade<F, NS, true>(S, cam, RP, P, s, valid, partials, counters, segs, paths, wb_next, wb_end);
             }
         } else if constexpr (!LITE) {
             if (phase == 0) pool_node<F, NS, false>(S, P, s, valid, n_take);
             else if (phase == 1) pool_prim<F, NS, false>(S, P, s, valid);
             else if (phase == 2) pool_inst<F, NS, false>(S, P, s, valid);
-            else pool_shade<F, NS, false>(S, cam, RP, P, s, valid, partials, counters, segs, paths);
+            else pool_shade<F, NS, false>(S, cam, RP, P, s, valid, partials, counters, segs, paths, wb_next, wb_end);
         }
     }
     // block-level reduction of the counters

@@ -76,17 +76,31 @@ struct RenderParams {
     uint32_t n_items;        // n_owned_pixels * n_chunks
     uint32_t n_slots;        // paths in flight
     uint32_t rank, world, rows_per_block;
-    FastDiv div_pixels, div_width, div_rows;  // by n_owned_pixels, image width, rows_per_block
+    FastDiv div_pixels, div_rows;  // by n_owned_pixels, rows_per_block
+    FastDiv div_strip, div_last;   // by width * NRRT_TILE_ROWS (pixels of a full strip), by the rows of the last strip
+    uint32_t full_strips;          // strips of NRRT_TILE_ROWS owned rows
 };
 
-// owned pixel index -> (x, y): rank owns row-blocks b with b % world == rank
+// owned pixel index -> (x, y) and the owned row j: rank owns row-blocks b with b % world == rank.
+// Owned pixels are numbered in STRIPS of NRRT_TILE_ROWS owned rows, column by column inside a strip, so that a run of
+// consecutive indices — the block of work items a warp takes (NRRT_ITEM_BLOCK = 128 = 16 columns x 8 rows) — is a
+// compact tile of the image instead of a 128-pixel piece of one row: rays of neighbouring lanes see the same part of
+// the tree and the same materials.  The last strip may be shorter (its height divides differently).
+#ifndef NRRT_TILE_ROWS
+#define NRRT_TILE_ROWS 8
+#endif
 __device__ __forceinline__ void owned_pixel(const nrrt_camera& cam, const RenderParams& P, uint32_t po, uint32_t& x,
-                                            uint32_t& y) {
-    uint32_t W = cam.width;
-    uint32_t j = P.div_width.div(po);
-    x = po - j * W;
-    uint32_t b = P.div_rows.div(j), r = j - b * P.rows_per_block;
-    y = (b * P.world + P.rank) * P.rows_per_block + r;
+                                            uint32_t& y, uint32_t& j) {
+    const uint32_t strip = P.div_strip.div(po), k = po - strip * P.div_strip.d;  // div_strip.d = W * NRRT_TILE_ROWS
+    uint32_t r;
+    if (strip < P.full_strips) {
+        x = k / NRRT_TILE_ROWS, r = k % NRRT_TILE_ROWS;
+    } else {
+        x = P.div_last.div(k), r = k - x * P.div_last.d;  // the cut-off last strip: div_last.d rows
+    }
+    j = strip * NRRT_TILE_ROWS + r;
+    const uint32_t b = P.div_rows.div(j), rr = j - b * P.rows_per_block;
+    y = (b * P.world + P.rank) * P.rows_per_block + rr;
 }
 
 struct WorkItem {
@@ -97,7 +111,8 @@ struct WorkItem {
 __device__ __forceinline__ uint32_t decode_item(const nrrt_camera& cam, const RenderParams& P, uint32_t item,
                                                 WorkItem& wi) {
     uint32_t c = P.div_pixels.div(item), po = item - c * P.n_owned_pixels;
-    owned_pixel(cam, P, po, wi.x, wi.y);
+    uint32_t j;
+    owned_pixel(cam, P, po, wi.x, wi.y, j);
     const uint32_t spp = cam.samples_per_pixel;
     if (c < P.n_eq) {
         wi.sample_end = (c + 1) * P.chunk;
@@ -293,9 +308,9 @@ __global__ void k_resolve(const __grid_constant__ nrrt_camera cam, const __grid_
         s = add3(s, mk3(partials[b], partials[b + 1], partials[b + 2]));
     }
     d3 col = div3(s, (double)cam.samples_per_pixel);
-    uint32_t x, y;
-    owned_pixel(cam, P, po, x, y);
-    size_t ob = (packed ? (size_t)po : (size_t)y * cam.width + x) * 3;  // owned pixels are numbered in ascending row order
+    uint32_t x, y, j;
+    owned_pixel(cam, P, po, x, y, j);
+    size_t ob = ((size_t)(packed ? j : y) * cam.width + x) * 3;  // packed: the rank's rows in ascending order
     out[ob] = (float)col.x, out[ob + 1] = (float)col.y, out[ob + 2] = (float)col.z;
 }
 
@@ -1610,12 +1625,21 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     const uint32_t want_slots = o.max_slots ? o.max_slots : (1u << 21);
     P.n_slots = (uint32_t)std::min<uint64_t>(n_items64, want_slots);
     P.div_pixels = FastDiv::make(P.n_owned_pixels);
-    P.div_width = FastDiv::make(W);
     P.div_rows = FastDiv::make(o.rows_per_block);
+    {
+        const uint32_t rows = P.n_owned_pixels / W;
+        if ((uint64_t)W * NRRT_TILE_ROWS > 0x7FFFFFFFull) {
+            ctx->err = "image too wide";
+            return NRRT_ERR_LIMIT;
+        }
+        P.div_strip = FastDiv::make(W * NRRT_TILE_ROWS);
+        P.full_strips = rows / NRRT_TILE_ROWS;
+        P.div_last = FastDiv::make(std::max<uint32_t>(rows % NRRT_TILE_ROWS, 1));
+    }
     for (uint32_t probe : {0u, 1u, W - 1, W, W + 1, P.n_owned_pixels - 1, P.n_owned_pixels, P.n_items - 1, 0x7fffffffu,
                            0xfffffff0u}) {  // the multiply-shift must agree with '/' (cheap self-check)
-        if (P.div_pixels.div(probe) != probe / P.div_pixels.d || P.div_width.div(probe) != probe / P.div_width.d ||
-            P.div_rows.div(probe) != probe / P.div_rows.d) {
+        if (P.div_pixels.div(probe) != probe / P.div_pixels.d || P.div_strip.div(probe) != probe / P.div_strip.d ||
+            P.div_rows.div(probe) != probe / P.div_rows.d || P.div_last.div(probe) != probe / P.div_last.d) {
             ctx->err = "internal error: FastDiv self-check failed";
             return NRRT_ERR_INVALID;
         }

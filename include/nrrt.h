@@ -475,6 +475,11 @@ int nrrt_render_multi(const int* devices, int n_devices, const nrrt_scene_desc* 
 int nrrt_encode_rgb8(nrrt_ctx* ctx, const float* rgb, uint32_t width, uint32_t height, float gamma, uint32_t flags,
                      uint8_t* out_rgb8);
 
+/* The work items of a pixel: a render sums a pixel's samples chunk by chunk, and the chunks depend only on spp and the
+ * size of the whole image (never on the partition, so an N-GPU image is the 1-GPU image bit for bit).  Writes the first
+ * sample of every chunk and spp as the last entry (n_chunks + 1 values, at most `max`); returns n_chunks. */
+uint32_t nrrt_chunk_starts(uint32_t samples_per_pixel, uint64_t total_pixels, uint32_t* starts, uint32_t max);
+
 /* sizeof() of the ABI structs as compiled (which = 0..18: object, material, texture,
  * image, graph_desc, camera_config, camera, node, box, xform, instance, scene_desc, hit, trace_stats,
  * render_opts, render_stats, camera_file, wnode, hit_compact) so a binding can verify its mirror of this header. */

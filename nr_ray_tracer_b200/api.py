@@ -72,6 +72,8 @@ def lib() -> C.CDLL:
         L.nrrt_render_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(A.SceneDesc), C.POINTER(A.Camera),
                                         C.POINTER(A.RenderOpts), C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.POINTER(A.RenderStats), C.c_char_p, C.c_size_t]
+        L.nrrt_chunk_starts.restype = C.c_uint32
+        L.nrrt_chunk_starts.argtypes = [C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32]
         L.nrrt_abi_sizeof.restype = C.c_size_t
         L.nrrt_abi_sizeof.argtypes = [C.c_int]
         _lib = L
@@ -81,6 +83,13 @@ def lib() -> C.CDLL:
 ABI_STRUCTS = [A.Object, A.Material, A.Texture, A.Image, A.GraphDesc, A.CameraConfig, A.Camera, A.Node, A.Box,
                A.Xform, A.Instance, A.SceneDesc, A.Hit, A.TraceStats, A.RenderOpts, A.RenderStats, A.CameraFile, A.WNode,
                A.HitCompact]
+
+
+def chunk_starts(samples_per_pixel: int, total_pixels: int):
+    """First sample of every work-item chunk of a pixel, and spp as the last entry (nrrt_chunk_starts)."""
+    buf = (C.c_uint32 * 64)()
+    n = lib().nrrt_chunk_starts(samples_per_pixel, total_pixels, buf, 64)
+    return [int(buf[i]) for i in range(n + 1)]
 
 
 def camera_build(cfg: A.CameraConfig) -> A.Camera:

@@ -1544,6 +1544,44 @@ int nrrt_trace_rays(nrrt_ctx* ctx, const double* rays, uint64_t n, double tmin, 
     return NRRT_OK;
 }
 
+// The chunks of a pixel (see nrrt_render): n_eq equal chunks of `chunk` samples, then halving chunks over the rest.
+// Closed form, so the kernels need no table (decode_item).
+static void chunk_schedule(uint32_t spp, uint64_t total_pixels, uint32_t& chunk, uint32_t& n_eq, uint32_t& n_chunks) {
+    if (spp < 1) spp = 1;
+    uint32_t eq_parts = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(8, 60000000ull / std::max<uint64_t>(total_pixels, 1)));
+    uint32_t tail_shift = 4, tail_max = 4;  // the last 1/16 of the samples in up to four halving chunks
+    if (const char* e = std::getenv("NRRT_CHUNKS")) std::sscanf(e, "%u,%u,%u", &eq_parts, &tail_shift, &tail_max);  // developer override
+    uint32_t R = tail_max ? (spp >> std::min<uint32_t>(tail_shift, 31)) : 0;   // samples left to the halving tail
+    if (eq_parts == 0) R = spp;
+    const uint32_t head = spp - R;
+    chunk = eq_parts ? std::max<uint32_t>(1, (head + eq_parts - 1) / eq_parts) : 1;
+    n_eq = eq_parts ? head / chunk : 0;            // whole equal chunks; what they leave over joins the tail
+    R = spp - n_eq * chunk;
+    uint32_t n_tail = R ? 1 : 0;
+    while (n_tail && n_tail < std::max<uint32_t>(tail_max, 1) && (R >> n_tail) >= 1) ++n_tail;
+    n_chunks = n_eq + n_tail;
+    if (n_chunks == 0) n_chunks = 1, n_eq = 0;     // spp >= 1 always gives at least one chunk; belt and braces
+}
+
+// Work-item layout of a render, for bindings and tests: writes the first sample of every chunk of a pixel and spp as
+// the last entry (n_chunks + 1 values, at most `max`); returns n_chunks.  Depends on spp and the image size only.
+uint32_t nrrt_chunk_starts(uint32_t samples_per_pixel, uint64_t total_pixels, uint32_t* starts, uint32_t max) {
+    const uint32_t spp = std::max<uint32_t>(samples_per_pixel, 1);
+    uint32_t chunk = 0, n_eq = 0, n = 0;
+    chunk_schedule(spp, total_pixels, chunk, n_eq, n);
+    for (uint32_t c = 0; c <= n && starts && c < max; ++c) {
+        uint32_t first;
+        if (c == n) first = spp;
+        else if (c < n_eq) first = c * chunk;
+        else {
+            const uint32_t base = n_eq * chunk, R = spp - base, k = c - n_eq;
+            first = base + R - (R >> k);
+        }
+        starts[c] = first;
+    }
+    return n;
+}
+
 static uint32_t owned_rows(uint32_t H, uint32_t rank, uint32_t world, uint32_t R) {
     uint32_t rows = 0;
     for (uint32_t b = rank; (uint64_t)b * R < H; b += world) rows += std::min<uint32_t>(R, H - b * R);
@@ -1600,22 +1638,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     //    lose to; so the last 1/16 of a pixel's samples goes in up to four HALVING chunks;
     //  * each item costs 24 B of scratch: up to 16 equal chunks for images up to 3.7 Mpixel, 8 at 4K (1080p x 1024
     //    spp: 15 x 60, then 62, 31, 16, 15; 4K x 4096 spp: 12 items per pixel, 2.4 GB where round 1 needed 6.4 GB).
-    {   // closed form, so the kernels need no table
-        const uint32_t spp = c.samples_per_pixel;
-        uint32_t eq_parts = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(8, 60000000ull / std::max<uint64_t>(total_pixels, 1)));
-        uint32_t tail_shift = 4, tail_max = 4;  // the last 1/16 of the samples in up to four halving chunks
-        if (const char* e = std::getenv("NRRT_CHUNKS")) std::sscanf(e, "%u,%u,%u", &eq_parts, &tail_shift, &tail_max);  // developer override
-        uint32_t R = tail_max ? (spp >> tail_shift) : 0;   // samples left to the halving tail
-        if (eq_parts == 0) R = spp;
-        const uint32_t head = spp - R;
-        P.chunk = eq_parts ? std::max<uint32_t>(1, (head + eq_parts - 1) / eq_parts) : 1;
-        P.n_eq = eq_parts ? head / P.chunk : 0;            // whole equal chunks; what they leave over joins the tail
-        R = spp - P.n_eq * P.chunk;
-        uint32_t n_tail = R ? 1 : 0;
-        while (n_tail && n_tail < std::max<uint32_t>(tail_max, 1) && (R >> n_tail) >= 1) ++n_tail;
-        P.n_chunks = P.n_eq + n_tail;
-        if (P.n_chunks == 0) P.n_chunks = 1, P.n_eq = 0;   // spp >= 1 always gives at least one chunk; belt and braces
-    }
+    chunk_schedule(c.samples_per_pixel, total_pixels, P.chunk, P.n_eq, P.n_chunks);
     const uint64_t n_items64 = (uint64_t)P.n_owned_pixels * P.n_chunks;
     if (n_items64 > 0xFFFFFFF0ull) {
         ctx->err = "too many work items";

@@ -122,6 +122,7 @@ extern "C" {
                              err: *mut c_char, err_len: usize) -> c_int;
     pub fn nrrt_encode_rgb8(ctx: *mut nrrt_ctx, rgb: *const f32, width: u32, height: u32, gamma: f32, flags: u32,
                             out_rgb8: *mut u8) -> c_int;
+    pub fn nrrt_chunk_starts(samples_per_pixel: u32, total_pixels: u64, starts: *mut u32, max: u32) -> u32;
     pub fn nrrt_abi_sizeof(which: c_int) -> usize;
 }
 '''

@@ -26,6 +26,10 @@
 #include "rt_device.cuh"
 
 #define NRRT_BLOCK 128
+#define NRRT_NO_ITEM 0xFFFFFFFFu
+#ifndef NRRT_ITEM_BLOCK
+#define NRRT_ITEM_BLOCK 128  // work items a warp takes from the global counter at a time (at most)
+#endif
 #ifndef NRRT_SPLIT_QUEUE
 #define NRRT_SPLIT_QUEUE 0  // 1: camera rays and bounce rays occupy separate regions of the ray queue.
 // Measured on B200 (round 1): splitting is 3.4x SLOWER (Cornell 3439 -> 994 Mseg/s, earth 4941 -> 1263).  With one
@@ -75,6 +79,7 @@ struct RenderParams {
     uint32_t n_chunks;       // work items per pixel = n_eq + the halving chunks over the remaining samples
     uint32_t n_items;        // n_owned_pixels * n_chunks
     uint32_t n_slots;        // paths in flight
+    uint32_t n_warps;        // warps that fetch work-item blocks (persistent kernels)
     uint32_t rank, world, rows_per_block;
     FastDiv div_pixels, div_rows;  // by n_owned_pixels, rows_per_block
     FastDiv div_strip, div_last;   // by width * NRRT_TILE_ROWS (pixels of a full strip), by the rows of the last strip
@@ -101,6 +106,16 @@ __device__ __forceinline__ void owned_pixel(const nrrt_camera& cam, const Render
     j = strip * NRRT_TILE_ROWS + r;
     const uint32_t b = P.div_rows.div(j), rr = j - b * P.rows_per_block;
     y = (b * P.world + P.rank) * P.rows_per_block + rr;
+}
+
+// Size of the next block of work items a warp takes: NRRT_ITEM_BLOCK while work is plentiful, shrinking to 32 (one per
+// lane) as the image runs out — so that the render does not end with a few warps still holding four items per lane
+// (a 400x225 image is 9 ms of work: blocks of 128 to the end cost it 20 %).  `next` is the global counter as last seen.
+__device__ __forceinline__ uint32_t item_block_size(const RenderParams& P, unsigned long long next, uint32_t need) {
+    const uint32_t left = next < P.n_items ? P.n_items - (uint32_t)next : 0u;
+    uint32_t b = left / (2u * max(P.n_warps, 1u));
+    b = min(max(b, 32u), (uint32_t)NRRT_ITEM_BLOCK);
+    return max(b, need);
 }
 
 struct WorkItem {
@@ -332,10 +347,6 @@ __global__ void k_encode_rgb8(const float* __restrict__ rgb, size_t n, float gam
 // attributes, object-space ray, time: 27 doubles per thread), so neither rays nor hit records ever round-trip
 // through HBM and there is no queue, no compaction and a single launch.  Traversal and shading use the same device functions as the
 // wavefront kernels and the same (pixel, sample-chunk) work items, so the image is bit-identical.
-#define NRRT_NO_ITEM 0xFFFFFFFFu
-#ifndef NRRT_ITEM_BLOCK
-#define NRRT_ITEM_BLOCK 128  // work items a warp takes from the global counter at a time
-#endif
 #ifndef NRRT_FUSED_MIN
 #define NRRT_FUSED_MIN 24  // lanes of a warp that must be waiting before a shading round runs.  Measured on B200, round 2
                            // (Cornell / spheres / noise / earth, Mrays/s; profiles/r02_fused_quorum_sweep.log): 16 6173 / 4558 /
@@ -459,14 +470,18 @@ k_render_fused(const __grid_constant__ DevScene S, const __grid_constant__ nrrt_
                 if (need) {
                     const uint32_t lane = threadIdx.x & 31u, n = __popc(need), rank = __popc(need & ((1u << lane) - 1u));
                     const uint32_t avail = wb_end - wb_next;
-                    uint32_t fresh_base = 0;
+                    uint32_t fresh_base = 0, fresh_size = 0;
                     if (n > avail) {
                         const uint32_t leader = __ffs(need) - 1;
-                        if (lane == leader) fresh_base = (uint32_t)atomicAdd(&counters[5], (unsigned long long)NRRT_ITEM_BLOCK);
+                        if (lane == leader) {
+                            fresh_size = item_block_size(P, *(volatile unsigned long long*)&counters[5], n - avail);
+                            fresh_base = (uint32_t)atomicAdd(&counters[5], (unsigned long long)fresh_size);
+                        }
                         fresh_base = __shfl_sync(0xffffffffu, fresh_base, leader);
+                        fresh_size = __shfl_sync(0xffffffffu, fresh_size, leader);
                     }
                     if (want) s_item = rank < avail ? wb_next + rank : fresh_base + (rank - avail);
-                    if (n > avail) wb_next = fresh_base + (n - avail), wb_end = fresh_base + NRRT_ITEM_BLOCK;
+                    if (n > avail) wb_next = fresh_base + (n - avail), wb_end = fresh_base + fresh_size;
                     else wb_next += n;
                 }
             }
@@ -1704,6 +1719,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
         const uint64_t resident = (uint64_t)(ctx->persistent_blocks / NRRT_EXTEND_MINBLOCKS) * NRRT_FUSED_BLOCKS_PER_SM * NRRT_BLOCK;
         P.n_slots = (uint32_t)std::min<uint64_t>(n_items64, o.max_slots ? std::min<uint64_t>(o.max_slots, resident) : resident);
     }
+    P.n_warps = pooled ? (P.n_slots + NRRT_POOL_NS - 1) / NRRT_POOL_NS : (P.n_slots + 31) / 32;
     const size_t fb_bytes = (size_t)total_pixels * 3 * sizeof(float);
     const size_t n = P.n_slots;
     // scratch layout

@@ -532,14 +532,18 @@ __device__ __forceinline__ void pool_shade(const DevScene& S, const nrrt_camera&
         if (need) {
             const uint32_t lane = threadIdx.x & 31u, n = __popc(need), rank = __popc(need & ((1u << lane) - 1u));
             const uint32_t avail = wb_end - wb_next;
-            uint32_t fresh_base = 0;
+            uint32_t fresh_base = 0, fresh_size = 0;
             if (n > avail) {
                 const uint32_t leader = __ffs(need) - 1;
-                if (lane == leader) fresh_base = (uint32_t)atomicAdd(&counters[5], (unsigned long long)NRRT_ITEM_BLOCK);
+                if (lane == leader) {
+                    fresh_size = item_block_size(RP, *(volatile unsigned long long*)&counters[5], n - avail);
+                    fresh_base = (uint32_t)atomicAdd(&counters[5], (unsigned long long)fresh_size);
+                }
                 fresh_base = __shfl_sync(0xffffffffu, fresh_base, leader);
+                fresh_size = __shfl_sync(0xffffffffu, fresh_size, leader);
             }
             if (want) item = rank < avail ? wb_next + rank : fresh_base + (rank - avail);
-            if (n > avail) wb_next = fresh_base + (n - avail), wb_end = fresh_base + NRRT_ITEM_BLOCK;
+            if (n > avail) wb_next = fresh_base + (n - avail), wb_end = fresh_base + fresh_size;
             else wb_next += n;
         }
     }

@@ -1963,11 +1963,12 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
 
 // rows of one rank, packed -> their places in the full image (device-output form of nrrt_render_multi)
 __global__ void k_place_rows(const float* __restrict__ packed, float* __restrict__ full, uint32_t row_floats, uint32_t n_rows,
-                             uint32_t rank, uint32_t world) {
+                             uint32_t rank, uint32_t world, uint32_t rows_per_block) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)n_rows * row_floats) return;
     const uint32_t k = (uint32_t)(i / row_floats), c = (uint32_t)(i - (size_t)k * row_floats);
-    full[((size_t)k * world + rank) * row_floats + c] = packed[i];
+    const uint32_t b = k / rows_per_block, r = k - b * rows_per_block;  // packed row k = row r of the rank's block b
+    full[((size_t)(b * world + rank) * rows_per_block + r) * row_floats + c] = packed[i];
 }
 
 int nrrt_render_multi(const int* devices, int n_devices, const nrrt_scene_desc* scene, const nrrt_camera* camera,
@@ -2022,9 +2023,9 @@ int nrrt_render_multi(const int* devices, int n_devices, const nrrt_scene_desc* 
             return;
         }
         nrrt_render_opts o = base;
-        o.rank = r, o.world = world, o.rows_per_block = world > 1 ? 1 : 0;
+        o.rank = r, o.world = world, o.rows_per_block = NRRT_TILE_ROWS;  // row-blocks = the kernels' tile height: compact tiles
         float* out = out_rgb;
-        R.n_rows = owned_rows(H, r, world, world > 1 ? 1 : 8);
+        R.n_rows = owned_rows(H, r, world, NRRT_TILE_ROWS);
         if (out_dev && world > 1) {  // packed rows on this device, gathered on devices[0] below
             if (cudaMalloc((void**)&R.d_packed, std::max<size_t>(1, (size_t)R.n_rows * row_floats * sizeof(float))) != cudaSuccess) {
                 R.rc = NRRT_ERR_CUDA, R.msg = "cudaMalloc (packed rows)";
@@ -2063,7 +2064,7 @@ int nrrt_render_multi(const int* devices, int n_devices, const nrrt_scene_desc* 
             }
             if (e != cudaSuccess) break;
             const size_t n = (size_t)R.n_rows * row_floats;
-            k_place_rows<<<(unsigned)((n + 255) / 256), 256>>>(src, out_rgb, (uint32_t)row_floats, R.n_rows, r, world);
+            k_place_rows<<<(unsigned)((n + 255) / 256), 256>>>(src, out_rgb, (uint32_t)row_floats, R.n_rows, r, world, NRRT_TILE_ROWS);
             e = cudaGetLastError();
             if (e == cudaSuccess) e = cudaDeviceSynchronize();
         }

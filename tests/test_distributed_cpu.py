@@ -62,13 +62,13 @@ def _worker(rank, world, port, H, W, R, out_path):
 
 def _worker_packed(rank, world, port, H, W, out_path):
     """The production path: rows rendered PACKED into FramebufferGather.packed (NRRT_RENDER_OUT_PACKED layout: the
-    rank's rows in ascending order), single-row interleave, one gather, one index_select on rank 0."""
+    rank's rows in ascending order), the production row-block height, one gather, one index_select on rank 0."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         R = D.rows_per_block_for(world)
-        assert R == 1
+        assert R == D.DEFAULT_ROWS_PER_BLOCK == 8   # = the kernels' tile height (compact 16 x 8 tiles)
         G = D.FramebufferGather(H, W, rank, world, R, torch.device("cpu"))
         for rep in range(2):  # buffers are reused across calls
             rows = D.owned_rows(H, rank, world, R)
@@ -88,8 +88,8 @@ def _worker_packed(rank, world, port, H, W, out_path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,H", [(2, 9), (3, 10)])
-def test_gloo_packed_gather_with_single_row_interleave(tmp_path, world, H):
+@pytest.mark.parametrize("world,H", [(2, 21), (3, 50)])
+def test_gloo_packed_gather_of_row_blocks(tmp_path, world, H):
     out_path = str(tmp_path / "full.npy")
     mp.spawn(_worker_packed, args=(world, _free_port(), H, 5, out_path), nprocs=world, join=True)
     assert np.load(out_path).shape == (H, 5, 3)

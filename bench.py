@@ -361,7 +361,9 @@ def run_b200(args):
         try:
             nt = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             k = nt[kernel_name]
-            traffic = k["dram_bytes_per_segment"] * (my_segs / max(ext_launches, 1))
+            # DRAM traffic of this kernel is the per-item partial sums: it scales with the image, not with spp / segments
+            iw, ih = k.get("image", [1920, 1080])
+            traffic = k["dram_bytes"] * (W * H) / float(iw * ih) / world
             issue_pct, lanes = k.get("issue_slot_utilisation_pct"), k.get("active_threads_per_instruction")
             capture = k.get("source")
         except (OSError, ValueError, KeyError):
@@ -373,8 +375,9 @@ def run_b200(args):
             "peak_source": f"traversal-only microbenchmark measured in this run: {n_rays} coherent primary rays of the same "
                            "camera through nrrt_trace_rays (NRRT_TRACE_COMPACT: closest hit only, 16 B out per ray), best of 6",
             "traffic": traffic,
-            "traffic_source": f"profiles/ncu_traffic.json <- {capture}: dram__bytes_read.sum + dram__bytes_write.sum per "
-                              "segment of the same kernel x segments per launch of this run",
+            "traffic_source": f"profiles/ncu_traffic.json <- {capture}: dram__bytes_read.sum + dram__bytes_write.sum of one launch of "
+                              "the same kernel on the same scene and image size (the traffic is the per-item partial sums: it "
+                              "scales with the image, not with spp), per rank",
             "ncu_issue_slot_utilisation_pct": issue_pct, "ncu_active_threads_per_instruction": lanes,
             "ncu_useful_lane_slot_frac": (issue_pct / 100.0 * lanes / 32.0) if issue_pct and lanes else None,
             "why_issue": "the scene (KB-MB) lives in L1/L2 and path state in shared memory; DRAM sees only the per-item partial "

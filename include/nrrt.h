@@ -454,7 +454,7 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* camera, const nrrt_render_opts
 
 /* Camera::render over several GPUs of one box from ONE process (what `nr-ray-tracer render --gpus N` calls; the
  * one-process-per-GPU form with torch.distributed / NCCL is nr_ray_tracer_b200/distributed.py).  One host thread and
- * one context per device: every device uploads the scene, renders the 8-row blocks b with b % n_devices == its index
+ * one context per device: every device uploads the scene, renders the rows r with r % n_devices == its index
  * end to end (same Philox streams, so the image is bit-identical to a single-GPU render) and the rows are brought
  * together inside the library:
  *   - host out_rgb (default): each device copies its rows straight into the caller's image with one strided D2H

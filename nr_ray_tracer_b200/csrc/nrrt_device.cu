@@ -82,28 +82,31 @@ struct RenderParams {
     uint32_t n_warps;        // warps that fetch work-item blocks (persistent kernels)
     uint32_t rank, world, rows_per_block;
     FastDiv div_pixels, div_rows;  // by n_owned_pixels, rows_per_block
-    FastDiv div_strip, div_last;   // by width * NRRT_TILE_ROWS (pixels of a full strip), by the rows of the last strip
-    uint32_t full_strips;          // strips of NRRT_TILE_ROWS owned rows
+    FastDiv div_tile, div_strip, div_last;  // by tile_rows, by width * tile_rows (pixels of a full strip), by the rows of the last strip
+    uint32_t full_strips;          // strips of tile_rows owned rows
 };
 
 // owned pixel index -> (x, y) and the owned row j: rank owns row-blocks b with b % world == rank.
-// Owned pixels are numbered in STRIPS of NRRT_TILE_ROWS owned rows, column by column inside a strip, so that a run of
-// consecutive indices — the block of work items a warp takes (NRRT_ITEM_BLOCK = 128 = 16 columns x 8 rows) — is a
-// compact tile of the image instead of a 128-pixel piece of one row: rays of neighbouring lanes see the same part of
-// the tree and the same materials.  The last strip may be shorter (its height divides differently).
+// Owned pixels are numbered in STRIPS of tile_rows owned rows, column by column inside a strip, so that a run of
+// consecutive indices — the block of work items a warp takes (NRRT_ITEM_BLOCK = 128) — is a compact tile of the image
+// (16 columns x 8 rows on one GPU): rays of neighbouring lanes see the same part of the tree and the same materials.
+// tile_rows = the largest divisor of rows_per_block up to NRRT_TILE_ROWS, so a tile never straddles two row-blocks —
+// which in a shared image lie `world` blocks apart (measured at N = 8 with single-row blocks and 8-row tiles: a tile
+// stretched over 64 image rows and the render lost all the coherence gain).  With single rows the tile is a 128-pixel
+// piece of one row, which is nearly as good (Cornell -0.4 %, teapot -1.8 % on one GPU).  The last strip may be shorter.
 #ifndef NRRT_TILE_ROWS
 #define NRRT_TILE_ROWS 8
 #endif
 __device__ __forceinline__ void owned_pixel(const nrrt_camera& cam, const RenderParams& P, uint32_t po, uint32_t& x,
                                             uint32_t& y, uint32_t& j) {
-    const uint32_t strip = P.div_strip.div(po), k = po - strip * P.div_strip.d;  // div_strip.d = W * NRRT_TILE_ROWS
+    const uint32_t strip = P.div_strip.div(po), k = po - strip * P.div_strip.d;  // div_strip.d = W * tile_rows
     uint32_t r;
     if (strip < P.full_strips) {
-        x = k / NRRT_TILE_ROWS, r = k % NRRT_TILE_ROWS;
+        x = P.div_tile.div(k), r = k - x * P.div_tile.d;
     } else {
         x = P.div_last.div(k), r = k - x * P.div_last.d;  // the cut-off last strip: div_last.d rows
     }
-    j = strip * NRRT_TILE_ROWS + r;
+    j = strip * P.div_tile.d + r;
     const uint32_t b = P.div_rows.div(j), rr = j - b * P.rows_per_block;
     y = (b * P.world + P.rank) * P.rows_per_block + rr;
 }
@@ -111,8 +114,14 @@ __device__ __forceinline__ void owned_pixel(const nrrt_camera& cam, const Render
 // Size of the next block of work items a warp takes: NRRT_ITEM_BLOCK while work is plentiful, shrinking to 32 (one per
 // lane) as the image runs out — so that the render does not end with a few warps still holding four items per lane
 // (a 400x225 image is 9 ms of work: blocks of 128 to the end cost it 20 %).  `next` is the global counter as last seen.
+// Items are chunk-major and the equal chunks come first: the LONG items end at item n_eq * n_owned_pixels, and a warp
+// that has just taken 128 of them when they run out keeps the GPU waiting for 4 long items per lane while everyone
+// else is through the short tail chunks — so the blocks also shrink towards that point (measured at N = 8, where a
+// GPU has 130 ms of work: 7 ms lost without this).
 __device__ __forceinline__ uint32_t item_block_size(const RenderParams& P, unsigned long long next, uint32_t need) {
-    const uint32_t left = next < P.n_items ? P.n_items - (uint32_t)next : 0u;
+    const uint32_t long_end = P.n_eq * P.n_owned_pixels;  // (fits: n_items does)
+    const uint32_t end = next < long_end ? long_end : P.n_items;
+    const uint32_t left = next < end ? end - (uint32_t)next : 0u;
     uint32_t b = left / (2u * max(P.n_warps, 1u));
     b = min(max(b, 32u), (uint32_t)NRRT_ITEM_BLOCK);
     return max(b, need);
@@ -1563,8 +1572,8 @@ int nrrt_trace_rays(nrrt_ctx* ctx, const double* rays, uint64_t n, double tmin, 
 // Closed form, so the kernels need no table (decode_item).
 static void chunk_schedule(uint32_t spp, uint64_t total_pixels, uint32_t& chunk, uint32_t& n_eq, uint32_t& n_chunks) {
     if (spp < 1) spp = 1;
-    uint32_t eq_parts = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(8, 60000000ull / std::max<uint64_t>(total_pixels, 1)));
-    uint32_t tail_shift = 4, tail_max = 4;  // the last 1/16 of the samples in up to four halving chunks
+    uint32_t eq_parts = (uint32_t)std::min<uint64_t>(28, std::max<uint64_t>(8, 60000000ull / std::max<uint64_t>(total_pixels, 1)));
+    uint32_t tail_shift = 4, tail_max = 0;  // no halving tail by default (see nrrt_render); NRRT_CHUNKS=28,4,4 turns one on
     if (const char* e = std::getenv("NRRT_CHUNKS")) std::sscanf(e, "%u,%u,%u", &eq_parts, &tail_shift, &tail_max);  // developer override
     uint32_t R = tail_max ? (spp >> std::min<uint32_t>(tail_shift, 31)) : 0;   // samples left to the halving tail
     if (eq_parts == 0) R = spp;
@@ -1650,9 +1659,13 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     //    holds for any item size, and every scene gained 6-16 % (Cornell 6242 -> 6640, noise 4840 -> 5622, earth 11602
     //    -> 12850, teapot 2094 -> 2211 at test sizes; 6482 -> 7006 and 2101 -> 2304 at the benchmark sizes);
     //  * the render ENDS waiting for the last slots to finish their item, which is what eight GPUs sharing one image
-    //    lose to; so the last 1/16 of a pixel's samples goes in up to four HALVING chunks;
-    //  * each item costs 24 B of scratch: up to 16 equal chunks for images up to 3.7 Mpixel, 8 at 4K (1080p x 1024
-    //    spp: 15 x 60, then 62, 31, 16, 15; 4K x 4096 spp: 12 items per pixel, 2.4 GB where round 1 needed 6.4 GB).
+    //    lose to.  Ending a pixel on a few HALVING chunks (the last 1/16 of its samples as 40, 20, 10, 9) was built for
+    //    that and measured: it makes things worse — one rank's share of the benchmark image (tools/rank_time.py) runs at
+    //    6520 Mrays/s with the halving tail and 6743 without, the whole image at 6935 either way — so the schedule is
+    //    equal chunks only; what does help is shrinking the item BLOCKS towards the end (item_block_size);
+    //  * each item costs 24 B of scratch and sets how long the last warps run alone: up to 28 equal chunks for images
+    //    up to 2.1 Mpixel, 8 at 4K (1080p x 1024 spp: 27 x 37 + 25; 4K x 4096 spp: 8 items per pixel, 1.6 GB where
+    //    round 1 needed 6.4 GB).
     chunk_schedule(c.samples_per_pixel, total_pixels, P.chunk, P.n_eq, P.n_chunks);
     const uint64_t n_items64 = (uint64_t)P.n_owned_pixels * P.n_chunks;
     if (n_items64 > 0xFFFFFFF0ull) {
@@ -1666,18 +1679,23 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
     P.div_rows = FastDiv::make(o.rows_per_block);
     {
         const uint32_t rows = P.n_owned_pixels / W;
-        if ((uint64_t)W * NRRT_TILE_ROWS > 0x7FFFFFFFull) {
+        uint32_t tile_rows = 1;  // largest divisor of rows_per_block that is <= NRRT_TILE_ROWS
+        for (uint32_t t = 1; t <= NRRT_TILE_ROWS; ++t)
+            if (o.rows_per_block % t == 0) tile_rows = t;
+        if ((uint64_t)W * tile_rows > 0x7FFFFFFFull) {
             ctx->err = "image too wide";
             return NRRT_ERR_LIMIT;
         }
-        P.div_strip = FastDiv::make(W * NRRT_TILE_ROWS);
-        P.full_strips = rows / NRRT_TILE_ROWS;
-        P.div_last = FastDiv::make(std::max<uint32_t>(rows % NRRT_TILE_ROWS, 1));
+        P.div_tile = FastDiv::make(tile_rows);
+        P.div_strip = FastDiv::make(W * tile_rows);
+        P.full_strips = rows / tile_rows;
+        P.div_last = FastDiv::make(std::max<uint32_t>(rows % tile_rows, 1));
     }
     for (uint32_t probe : {0u, 1u, W - 1, W, W + 1, P.n_owned_pixels - 1, P.n_owned_pixels, P.n_items - 1, 0x7fffffffu,
                            0xfffffff0u}) {  // the multiply-shift must agree with '/' (cheap self-check)
         if (P.div_pixels.div(probe) != probe / P.div_pixels.d || P.div_strip.div(probe) != probe / P.div_strip.d ||
-            P.div_rows.div(probe) != probe / P.div_rows.d || P.div_last.div(probe) != probe / P.div_last.d) {
+            P.div_rows.div(probe) != probe / P.div_rows.d || P.div_last.div(probe) != probe / P.div_last.d ||
+            P.div_tile.div(probe) != probe / P.div_tile.d) {
             ctx->err = "internal error: FastDiv self-check failed";
             return NRRT_ERR_INVALID;
         }
@@ -2023,9 +2041,9 @@ int nrrt_render_multi(const int* devices, int n_devices, const nrrt_scene_desc* 
             return;
         }
         nrrt_render_opts o = base;
-        o.rank = r, o.world = world, o.rows_per_block = NRRT_TILE_ROWS;  // row-blocks = the kernels' tile height: compact tiles
+        o.rank = r, o.world = world, o.rows_per_block = world > 1 ? 1 : 0;  // single rows: every device gets the same share of every part of the image
         float* out = out_rgb;
-        R.n_rows = owned_rows(H, r, world, NRRT_TILE_ROWS);
+        R.n_rows = owned_rows(H, r, world, world > 1 ? 1 : 8);
         if (out_dev && world > 1) {  // packed rows on this device, gathered on devices[0] below
             if (cudaMalloc((void**)&R.d_packed, std::max<size_t>(1, (size_t)R.n_rows * row_floats * sizeof(float))) != cudaSuccess) {
                 R.rc = NRRT_ERR_CUDA, R.msg = "cudaMalloc (packed rows)";
@@ -2064,7 +2082,7 @@ int nrrt_render_multi(const int* devices, int n_devices, const nrrt_scene_desc* 
             }
             if (e != cudaSuccess) break;
             const size_t n = (size_t)R.n_rows * row_floats;
-            k_place_rows<<<(unsigned)((n + 255) / 256), 256>>>(src, out_rgb, (uint32_t)row_floats, R.n_rows, r, world, NRRT_TILE_ROWS);
+            k_place_rows<<<(unsigned)((n + 255) / 256), 256>>>(src, out_rgb, (uint32_t)row_floats, R.n_rows, r, world, 1u);
             e = cudaGetLastError();
             if (e == cudaSuccess) e = cudaDeviceSynchronize();
         }

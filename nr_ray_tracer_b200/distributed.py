@@ -9,11 +9,11 @@ What keeps the gather off the critical path (round 1 lost 4 % of the 8-GPU step 
   * the kernels write a rank's rows PACKED (NRRT_RENDER_OUT_PACKED), so there is no pack step;
   * every buffer and the row permutation are built once per (image size, world) and reused (`FramebufferGather`);
   * rank 0 receives all parts into one stacked buffer and places the rows with ONE index_select kernel;
-  * rows are interleaved in blocks of 8 for every world size: the kernels hand work to a warp as compact 16 x 8 pixel
-    tiles of the rank's rows (that coherence is worth 8-10 % of the render), and a tile is only compact if the rank's
-    rows are adjacent in the image.  (Single rows balance perfectly — 135 rows each at 1080p over 8 GPUs — but stretch
-    a tile over 64 image rows: measured, the 8-GPU render lost the whole coherence gain, 0.885 of linear.  Blocks of 8
-    cost 17 vs 16.875 blocks on the busiest rank: 0.7 %.)
+  * rows are interleaved singly for world > 1 (rows_per_block = 1): 1080 rows over 8 GPUs is 135 rows each, exactly, and
+    every rank gets the same share of every part of the image.  (Measured at N = 8: blocks of 8 rows leave 4 % between
+    the fastest and the slowest rank on the Cornell box — bright rows are cheap, floor rows are not — and the step waits
+    for the slowest.)  The kernels size their work tiles to the row-block (csrc/nrrt_device.cu owned_pixel): with single
+    rows a warp's block of 128 items is a 128-pixel piece of one row, so it stays compact in the image.
 
 The partition arithmetic here must match owned_pixel()/owned_rows() in csrc/nrrt_device.cu.
 """
@@ -29,8 +29,8 @@ DEFAULT_ROWS_PER_BLOCK = 8  # single-GPU default of the C ABI (any value gives t
 
 
 def rows_per_block_for(world: int) -> int:
-    """Row-block height used by render_distributed / bench.py (= the kernels' tile height, for every world size)."""
-    return DEFAULT_ROWS_PER_BLOCK
+    """Row-block height used by render_distributed / bench.py: single rows once the image is shared out."""
+    return 1 if world > 1 else DEFAULT_ROWS_PER_BLOCK
 
 
 def owned_row_ranges(height: int, rank: int, world: int, rows_per_block: int = DEFAULT_ROWS_PER_BLOCK

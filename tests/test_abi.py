@@ -96,16 +96,15 @@ def test_product_never_imports_oracle():
 
 def test_work_item_chunks_tile_the_samples_and_ignore_the_partition():
     """nrrt_chunk_starts: the chunks of a pixel cover [0, spp) exactly, none empty, for every spp; the schedule is a
-    function of spp and the whole image's size only (it has no rank / world argument at all), it ends on short chunks
-    (what a shared image waits for at the end), and its scratch stays bounded for large images."""
+    function of spp and the whole image's size only (it has no rank / world argument at all), and its scratch stays bounded for large images."""
     from nr_ray_tracer_b200 import api
     for pixels in (1, 90000, 1920 * 1080, 3840 * 2160, 2 ** 31 - 1):
         for spp in list(range(1, 260)) + [1000, 1024, 4096, 65535, 1 << 20]:
             st = api.chunk_starts(spp, pixels)
             assert st[0] == 0 and st[-1] == spp and all(a < b for a, b in zip(st, st[1:])), (pixels, spp, st)
-            assert len(st) - 1 <= 20
+            assert len(st) - 1 <= 32
     st = api.chunk_starts(1024, 1920 * 1080)
     sizes = [b - a for a, b in zip(st, st[1:])]
-    assert sizes == [60] * 16 + [32, 16, 8, 8]
-    assert len(api.chunk_starts(4096, 3840 * 2160)) - 1 == 12          # 4K: 8 equal + 4 halving
+    assert sizes == [37] * 27 + [25]
+    assert len(api.chunk_starts(4096, 3840 * 2160)) - 1 == 8           # 4K: 8 equal chunks
     assert api.chunk_starts(0, 100) == [0, 1]                          # spp clamps to 1 (camera.rs:104)

@@ -68,7 +68,7 @@ def _worker_packed(rank, world, port, H, W, out_path):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         R = D.rows_per_block_for(world)
-        assert R == D.DEFAULT_ROWS_PER_BLOCK == 8   # = the kernels' tile height (compact 16 x 8 tiles)
+        assert R == 1   # single rows: every rank gets the same share of every part of the image
         G = D.FramebufferGather(H, W, rank, world, R, torch.device("cpu"))
         for rep in range(2):  # buffers are reused across calls
             rows = D.owned_rows(H, rank, world, R)

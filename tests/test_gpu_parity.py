@@ -704,3 +704,42 @@ def test_checked_build_runs_clean(tmp_path):
                        cwd=root, env=dict(os.environ, NRRT_B200_LIB=lib), timeout=600)
     assert r.returncode == 0 and "sanitize_run done" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert "NRRT_CHECK failed" not in r.stdout + r.stderr
+
+
+def test_compact_trace_output_is_the_same_query(gpu_ctx):
+    """NRRT_TRACE_COMPACT (the traversal microbenchmark bench.py reports the render kernels against) is the same
+    closest-hit query as the full one: identical t and winning primitive, 16 bytes per ray, for both traversal modes."""
+    import torch
+    for name in ("cornell-box-scene.json", "utah-teapot-scene.json", "spheres.toml"):
+        g = load(name)
+        hs = _scene(gpu_ctx, g)
+        rays = np.concatenate([kat.random_rays(g, 20000), kat.aimed_rays(g, 20000), kat.special_rays(g)[:2000]])
+        full, _ = gpu_ctx.trace_rays(rays)
+        d_rays = torch.from_numpy(np.ascontiguousarray(rays)).cuda()
+        for visit_all in (False, True):
+            out = torch.zeros((len(rays), 16), dtype=torch.uint8, device="cuda")
+            gpu_ctx.trace_rays_device(d_rays.data_ptr(), len(rays), out.data_ptr(), compact=True, visit_all=visit_all)
+            torch.cuda.synchronize()
+            c = out.cpu().numpy().view(np.dtype([("t", "<f8"), ("prim", "<u4"), ("depth_inst0", "<u4")])).reshape(-1)
+            assert np.array_equal(c["prim"], full["prim"]), name
+            assert np.array_equal(c["t"], full["t"]), name
+            assert np.array_equal(c["depth_inst0"] & 7, full["depth"]), name
+        del hs
+
+
+def test_auto_mode_picks_the_measured_design_and_scene_render_is_the_same_call(gpu_ctx):
+    """NRRT_MODE_AUTO: pooled kernel on the mesh scenes, fused kernel on the small ones (stats.mode says which);
+    api.Scene.load(...).render() — the mirror of the reference's Scene::render — is that very path."""
+    from nr_ray_tracer_b200.scene_config import CameraConfig
+    for name, want in (("cornell-box-scene.json", A.MODE_FUSED), ("spheres.toml", A.MODE_FUSED),
+                       ("utah-teapot-scene.json", A.MODE_POOL), ("cornell-teapot-scene.json", A.MODE_POOL)):
+        g = load(name, width=64, height=36, samples_per_pixel=4)
+        hs = _scene(gpu_ctx, g)
+        cam = api.camera_build(g.camera.to_builder_config())
+        img, st = gpu_ctx.render(cam, seed=0)          # default mode = auto
+        assert st["mode"] == want, (name, st["mode"])
+        scene = api.Scene.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scenes", name),
+                               camera_override=CameraConfig(width=64, height=36, samples_per_pixel=4),
+                               base_dir=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), ctx=gpu_ctx)
+        assert np.array_equal(scene.render(seed=0), img) and scene.last_stats["mode"] == want
+        del hs

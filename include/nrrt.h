@@ -480,6 +480,14 @@ int nrrt_encode_rgb8(nrrt_ctx* ctx, const float* rgb, uint32_t width, uint32_t h
  * sample of every chunk and spp as the last entry (n_chunks + 1 values, at most `max`); returns n_chunks. */
 uint32_t nrrt_chunk_starts(uint32_t samples_per_pixel, uint64_t total_pixels, uint32_t* starts, uint32_t max);
 
+/* The work items of one rank's render, decoded by the functions the kernels use (nrrt_device.cu decode_item /
+ * owned_pixel): items [first, first + n) as 4 values each — x, y, first sample, one past the last sample — in the
+ * order they are handed out (chunk-major; inside a chunk the rank's pixels in strips of up to 8 rows, column by column).
+ * Returns the number of items of that render (owned pixels x chunks), 0 for arguments nrrt_render would refuse.
+ * For tests and bindings: every (owned pixel, sample) must appear exactly once, whatever the partition. */
+uint32_t nrrt_work_items(uint32_t width, uint32_t height, uint32_t samples_per_pixel, uint32_t rank, uint32_t world,
+                         uint32_t rows_per_block, uint32_t first, uint32_t n, uint32_t* out);
+
 /* sizeof() of the ABI structs as compiled (which = 0..18: object, material, texture,
  * image, graph_desc, camera_config, camera, node, box, xform, instance, scene_desc, hit, trace_stats,
  * render_opts, render_stats, camera_file, wnode, hit_compact) so a binding can verify its mirror of this header. */

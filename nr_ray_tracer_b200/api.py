@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
                                         C.POINTER(A.RenderStats), C.c_char_p, C.c_size_t]
         L.nrrt_chunk_starts.restype = C.c_uint32
         L.nrrt_chunk_starts.argtypes = [C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32]
+        L.nrrt_work_items.restype = C.c_uint32
+        L.nrrt_work_items.argtypes = [C.c_uint32] * 8 + [C.POINTER(C.c_uint32)]
         L.nrrt_abi_sizeof.restype = C.c_size_t
         L.nrrt_abi_sizeof.argtypes = [C.c_int]
         _lib = L
@@ -90,6 +92,18 @@ def chunk_starts(samples_per_pixel: int, total_pixels: int):
     buf = (C.c_uint32 * 64)()
     n = lib().nrrt_chunk_starts(samples_per_pixel, total_pixels, buf, 64)
     return [int(buf[i]) for i in range(n + 1)]
+
+
+def work_items(width: int, height: int, samples_per_pixel: int, rank: int = 0, world: int = 1,
+               rows_per_block: int = 8) -> np.ndarray:
+    """All work items of one rank's render in hand-out order, (n_items, 4) uint32: x, y, first sample, end sample
+    (nrrt_work_items: the kernels' own decode, run on the host)."""
+    n = lib().nrrt_work_items(width, height, samples_per_pixel, rank, world, rows_per_block, 0, 0, None)
+    out = np.zeros((n, 4), dtype=np.uint32)
+    if n:
+        lib().nrrt_work_items(width, height, samples_per_pixel, rank, world, rows_per_block, 0, n,
+                              out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return out
 
 
 def camera_build(cfg: A.CameraConfig) -> A.Camera:

@@ -97,7 +97,7 @@ struct RenderParams {
 #ifndef NRRT_TILE_ROWS
 #define NRRT_TILE_ROWS 8
 #endif
-__device__ __forceinline__ void owned_pixel(const nrrt_camera& cam, const RenderParams& P, uint32_t po, uint32_t& x,
+__host__ __device__ __forceinline__ void owned_pixel(const nrrt_camera& cam, const RenderParams& P, uint32_t po, uint32_t& x,
                                             uint32_t& y, uint32_t& j) {
     const uint32_t strip = P.div_strip.div(po), k = po - strip * P.div_strip.d;  // div_strip.d = W * tile_rows
     uint32_t r;
@@ -132,8 +132,8 @@ struct WorkItem {
     uint32_t sample_end;  // one past the last sample of the chunk
 };
 // item -> pixel + sample range; returns the first sample
-__device__ __forceinline__ uint32_t decode_item(const nrrt_camera& cam, const RenderParams& P, uint32_t item,
-                                                WorkItem& wi) {
+__host__ __device__ __forceinline__ uint32_t decode_item(const nrrt_camera& cam, const RenderParams& P, uint32_t item,
+                                                         WorkItem& wi) {
     uint32_t c = P.div_pixels.div(item), po = item - c * P.n_owned_pixels;
     uint32_t j;
     owned_pixel(cam, P, po, wi.x, wi.y, j);
@@ -1612,6 +1612,83 @@ static uint32_t owned_rows(uint32_t H, uint32_t rank, uint32_t world, uint32_t R
     return rows;
 }
 
+// Partition and work-item fields of RenderParams (everything decode_item / owned_pixel / item_block_size read, bar the
+// slot counts): shared by nrrt_render and nrrt_work_items.  Returns nullptr or the reason it cannot be done.
+static const char* work_item_params(RenderParams& P, uint32_t W, uint32_t H, uint32_t spp, uint32_t rank, uint32_t world,
+                                    uint32_t rows_per_block) {
+    const uint64_t total_pixels = (uint64_t)W * H;
+    P.rank = rank, P.world = world, P.rows_per_block = rows_per_block;
+    P.n_owned_pixels = owned_rows(H, rank, world, rows_per_block) * W;
+    // Work items of a pixel.  They fix the order in which its samples are summed, so they may depend only on what
+    // every rank of every partition agrees on — spp and the size of the WHOLE image — never on slots, rank or world:
+    // the image is then bit-identical for every slot count and GPU count.  Items are numbered chunk-major (every
+    // pixel's chunk 0, then every pixel's chunk 1, ...) and handed to a WARP in blocks of NRRT_ITEM_BLOCK consecutive
+    // ones, i.e. consecutive pixels of one chunk (see the kernels).  Measured (profiles/r02_chunk_schedules.log,
+    // r02_item_blocks_and_chunk_schedules.log):
+    //  * what matters most is that the lanes of a warp stay on neighbouring pixels — same materials, textures and
+    //    subtrees.  With one global counter and an item per lane that only held for tiny items (noise.toml: 5552
+    //    Mrays/s with 1-sample items, 4798 with 2-sample ones, 4361 with seven halving chunks); with per-warp blocks it
+    //    holds for any item size, and every scene gained 6-16 % (Cornell 6242 -> 6640, noise 4840 -> 5622, earth 11602
+    //    -> 12850, teapot 2094 -> 2211 at test sizes; 6482 -> 7006 and 2101 -> 2304 at the benchmark sizes);
+    //  * the render ENDS waiting for the last slots to finish their item, which is what eight GPUs sharing one image
+    //    lose to.  Ending a pixel on a few HALVING chunks (the last 1/16 of its samples as 40, 20, 10, 9) was built for
+    //    that and measured: it makes things worse — one rank's share of the benchmark image (tools/rank_time.py) runs at
+    //    6520 Mrays/s with the halving tail and 6743 without, the whole image at 6935 either way — so the schedule is
+    //    equal chunks only; what does help is shrinking the item BLOCKS towards the end (item_block_size);
+    //  * each item costs 24 B of scratch and sets how long the last warps run alone: up to 28 equal chunks for images
+    //    up to 2.1 Mpixel, 8 at 4K (1080p x 1024 spp: 27 x 37 + 25; 4K x 4096 spp: 8 items per pixel, 1.6 GB where
+    //    round 1 needed 6.4 GB).
+    chunk_schedule(spp, total_pixels, P.chunk, P.n_eq, P.n_chunks);
+    const uint64_t n_items64 = (uint64_t)P.n_owned_pixels * P.n_chunks;
+    if (n_items64 > 0xFFFFFFF0ull) return "too many work items";
+    P.n_items = (uint32_t)n_items64;
+    P.n_slots = P.n_warps = 0;
+    P.div_pixels = FastDiv::make(P.n_owned_pixels);
+    P.div_rows = FastDiv::make(rows_per_block);
+    {
+        const uint32_t rows = P.n_owned_pixels / W;
+        uint32_t tile_rows = 1;  // largest divisor of rows_per_block that is <= NRRT_TILE_ROWS
+        for (uint32_t t = 1; t <= NRRT_TILE_ROWS; ++t)
+            if (rows_per_block % t == 0) tile_rows = t;
+        if ((uint64_t)W * tile_rows > 0x7FFFFFFFull) return "image too wide";
+        P.div_tile = FastDiv::make(tile_rows);
+        P.div_strip = FastDiv::make(W * tile_rows);
+        P.full_strips = rows / tile_rows;
+        P.div_last = FastDiv::make(std::max<uint32_t>(rows % tile_rows, 1));
+    }
+    for (uint32_t probe : {0u, 1u, W - 1, W, W + 1, P.n_owned_pixels - 1, P.n_owned_pixels, P.n_items - 1, 0x7fffffffu,
+                           0xfffffff0u}) {  // the multiply-shift must agree with '/' (cheap self-check)
+        if (P.div_pixels.div(probe) != probe / P.div_pixels.d || P.div_strip.div(probe) != probe / P.div_strip.d ||
+            P.div_rows.div(probe) != probe / P.div_rows.d || P.div_last.div(probe) != probe / P.div_last.d ||
+            P.div_tile.div(probe) != probe / P.div_tile.d)
+            return "internal error: FastDiv self-check failed";
+    }
+    return nullptr;
+}
+
+// Work items [first, first + n) of one rank's render, decoded by the very functions the kernels use: 4 values per item
+// (x, y, first sample, one past the last sample).  Returns the number of items of that render, 0 if the arguments are
+// not ones nrrt_render would take.
+uint32_t nrrt_work_items(uint32_t width, uint32_t height, uint32_t samples_per_pixel, uint32_t rank, uint32_t world,
+                         uint32_t rows_per_block, uint32_t first, uint32_t n, uint32_t* out) {
+    if (width == 0 || height == 0 || (uint64_t)width * height > 0x7FFFFFFFull) return 0;
+    if (world == 0) world = 1;
+    if (rank >= world) return 0;
+    if (rows_per_block == 0) rows_per_block = 8;
+    RenderParams P;
+    P.key = make_uint2(0, 0);
+    nrrt_camera cam;
+    std::memset(&cam, 0, sizeof cam);
+    cam.width = width, cam.height = height, cam.samples_per_pixel = std::max<uint32_t>(samples_per_pixel, 1);
+    if (work_item_params(P, width, height, cam.samples_per_pixel, rank, world, rows_per_block)) return 0;
+    for (uint32_t i = 0; out && i < n && (uint64_t)first + i < P.n_items; ++i) {
+        WorkItem wi;
+        const uint32_t s0 = decode_item(cam, P, first + i, wi);
+        out[4 * i + 0] = wi.x, out[4 * i + 1] = wi.y, out[4 * i + 2] = s0, out[4 * i + 3] = wi.sample_end;
+    }
+    return P.n_items;
+}
+
 int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* opts_in, float* out_rgb,
                 nrrt_progress_fn progress, void* user, nrrt_render_stats* stats) {
     if (!ctx) return NRRT_ERR_INVALID;
@@ -1645,61 +1722,13 @@ int nrrt_render(nrrt_ctx* ctx, const nrrt_camera* cam, const nrrt_render_opts* o
 
     RenderParams P;
     P.key = make_uint2((uint32_t)o.seed, (uint32_t)(o.seed >> 32));
-    P.rank = o.rank, P.world = o.world, P.rows_per_block = o.rows_per_block;
-    P.n_owned_pixels = owned_rows(H, o.rank, o.world, o.rows_per_block) * W;
-    // Work items of a pixel.  They fix the order in which its samples are summed, so they may depend only on what
-    // every rank of every partition agrees on — spp and the size of the WHOLE image — never on slots, rank or world:
-    // the image is then bit-identical for every slot count and GPU count.  Items are numbered chunk-major (every
-    // pixel's chunk 0, then every pixel's chunk 1, ...) and handed to a WARP in blocks of NRRT_ITEM_BLOCK consecutive
-    // ones, i.e. consecutive pixels of one chunk (see the kernels).  Measured (profiles/r02_chunk_schedules.log,
-    // r02_item_blocks_and_chunk_schedules.log):
-    //  * what matters most is that the lanes of a warp stay on neighbouring pixels — same materials, textures and
-    //    subtrees.  With one global counter and an item per lane that only held for tiny items (noise.toml: 5552
-    //    Mrays/s with 1-sample items, 4798 with 2-sample ones, 4361 with seven halving chunks); with per-warp blocks it
-    //    holds for any item size, and every scene gained 6-16 % (Cornell 6242 -> 6640, noise 4840 -> 5622, earth 11602
-    //    -> 12850, teapot 2094 -> 2211 at test sizes; 6482 -> 7006 and 2101 -> 2304 at the benchmark sizes);
-    //  * the render ENDS waiting for the last slots to finish their item, which is what eight GPUs sharing one image
-    //    lose to.  Ending a pixel on a few HALVING chunks (the last 1/16 of its samples as 40, 20, 10, 9) was built for
-    //    that and measured: it makes things worse — one rank's share of the benchmark image (tools/rank_time.py) runs at
-    //    6520 Mrays/s with the halving tail and 6743 without, the whole image at 6935 either way — so the schedule is
-    //    equal chunks only; what does help is shrinking the item BLOCKS towards the end (item_block_size);
-    //  * each item costs 24 B of scratch and sets how long the last warps run alone: up to 28 equal chunks for images
-    //    up to 2.1 Mpixel, 8 at 4K (1080p x 1024 spp: 27 x 37 + 25; 4K x 4096 spp: 8 items per pixel, 1.6 GB where
-    //    round 1 needed 6.4 GB).
-    chunk_schedule(c.samples_per_pixel, total_pixels, P.chunk, P.n_eq, P.n_chunks);
-    const uint64_t n_items64 = (uint64_t)P.n_owned_pixels * P.n_chunks;
-    if (n_items64 > 0xFFFFFFF0ull) {
-        ctx->err = "too many work items";
-        return NRRT_ERR_LIMIT;
+    if (const char* why = work_item_params(P, W, H, c.samples_per_pixel, o.rank, o.world, o.rows_per_block)) {
+        ctx->err = why;
+        return std::strstr(why, "internal") ? NRRT_ERR_INVALID : NRRT_ERR_LIMIT;
     }
-    P.n_items = (uint32_t)n_items64;
+    const uint64_t n_items64 = P.n_items;
     const uint32_t want_slots = o.max_slots ? o.max_slots : (1u << 21);
     P.n_slots = (uint32_t)std::min<uint64_t>(n_items64, want_slots);
-    P.div_pixels = FastDiv::make(P.n_owned_pixels);
-    P.div_rows = FastDiv::make(o.rows_per_block);
-    {
-        const uint32_t rows = P.n_owned_pixels / W;
-        uint32_t tile_rows = 1;  // largest divisor of rows_per_block that is <= NRRT_TILE_ROWS
-        for (uint32_t t = 1; t <= NRRT_TILE_ROWS; ++t)
-            if (o.rows_per_block % t == 0) tile_rows = t;
-        if ((uint64_t)W * tile_rows > 0x7FFFFFFFull) {
-            ctx->err = "image too wide";
-            return NRRT_ERR_LIMIT;
-        }
-        P.div_tile = FastDiv::make(tile_rows);
-        P.div_strip = FastDiv::make(W * tile_rows);
-        P.full_strips = rows / tile_rows;
-        P.div_last = FastDiv::make(std::max<uint32_t>(rows % tile_rows, 1));
-    }
-    for (uint32_t probe : {0u, 1u, W - 1, W, W + 1, P.n_owned_pixels - 1, P.n_owned_pixels, P.n_items - 1, 0x7fffffffu,
-                           0xfffffff0u}) {  // the multiply-shift must agree with '/' (cheap self-check)
-        if (P.div_pixels.div(probe) != probe / P.div_pixels.d || P.div_strip.div(probe) != probe / P.div_strip.d ||
-            P.div_rows.div(probe) != probe / P.div_rows.d || P.div_last.div(probe) != probe / P.div_last.d ||
-            P.div_tile.div(probe) != probe / P.div_tile.d) {
-            ctx->err = "internal error: FastDiv self-check failed";
-            return NRRT_ERR_INVALID;
-        }
-    }
 
     const bool out_dev = (o.flags & NRRT_RENDER_OUT_DEVICE) != 0;
     const bool packed = (o.flags & NRRT_RENDER_OUT_PACKED) != 0;

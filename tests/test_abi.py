@@ -2,6 +2,8 @@
 layouts match the ctypes mirror, and it fails loudly (no fallback) when there is no GPU."""
 import ctypes as C
 import os
+
+import numpy as np
 import re
 
 import pytest
@@ -108,3 +110,49 @@ def test_work_item_chunks_tile_the_samples_and_ignore_the_partition():
     assert sizes == [37] * 27 + [25]
     assert len(api.chunk_starts(4096, 3840 * 2160)) - 1 == 8           # 4K: 8 equal chunks
     assert api.chunk_starts(0, 100) == [0, 1]                          # spp clamps to 1 (camera.rs:104)
+
+
+def test_work_items_cover_every_owned_pixel_and_sample_exactly_once():
+    """nrrt_work_items runs the kernels' own item decode (decode_item / owned_pixel, compiled for the host as well):
+    for every partition the items of all ranks together hold each (pixel, sample) of the image exactly once, a rank's
+    items lie on the rows distributed.owned_rows gives it, every pixel is cut at the chunk boundaries of
+    nrrt_chunk_starts, and items come chunk-major with the pixels of a chunk in compact tiles."""
+    from nr_ray_tracer_b200 import api
+    from nr_ray_tracer_b200 import distributed as D
+    cases = [(1, 1, 1), (1, 1, 257), (33, 17, 5), (64, 37, 40), (7, 100, 3), (400, 225, 9), (5, 3, 1000), (1, 64, 33),
+             (129, 9, 2)]
+    for W, H, spp in cases:
+        starts = api.chunk_starts(spp, W * H)
+        n_chunks = len(starts) - 1
+        for world, R in ((1, 8), (1, 1), (2, 1), (2, 8), (3, 2), (3, 5), (8, 1), (8, 8), (5, 12), (4, 16), (70, 1)):
+            seen = np.zeros((H, W), dtype=np.int64)          # samples of each pixel covered so far
+            for rank in range(world):
+                it = api.work_items(W, H, spp, rank, world, R).astype(np.int64)
+                rows = D.owned_rows(H, rank, world, R)
+                assert len(it) == len(rows) * W * n_chunks, (W, H, spp, world, R, rank)
+                if len(it) == 0:
+                    continue
+                x, y, s0, s1 = it.T
+                assert x.min() >= 0 and x.max() < W and np.isin(y, rows).all()
+                npx = len(rows) * W
+                c = np.arange(len(it)) // npx                 # chunk-major numbering
+                assert np.array_equal(s0, np.asarray(starts)[c]) and np.array_equal(s1, np.asarray(starts)[c + 1])
+                # every chunk visits the rank's pixels in the same order, each exactly once
+                first = y[:npx] * W + x[:npx]
+                assert len(np.unique(first)) == npx
+                assert np.array_equal((y * W + x).reshape(n_chunks, npx), np.broadcast_to(first, (n_chunks, npx)))
+                np.add.at(seen, (y, x), s1 - s0)
+            assert (seen == spp).all(), (W, H, spp, world, R)
+    # the tiles: on one GPU (row-blocks of 8) a run of 128 items is 16 columns x 8 rows; with single-row blocks
+    # (what a shared image uses) it is 128 pixels of one row
+    it = api.work_items(400, 225, 9).astype(np.int64)
+    blk = it[3 * 128:4 * 128]
+    assert np.ptp(blk[:, 0]) == 15 and np.ptp(blk[:, 1]) == 7 and len(np.unique(blk[:, 1] * 400 + blk[:, 0])) == 128
+    it = api.work_items(400, 225, 9, rank=3, world=8, rows_per_block=1).astype(np.int64)
+    blk = it[:128]
+    assert np.ptp(blk[:, 1]) == 0 and blk[0, 1] == 3 and np.array_equal(blk[:, 0], np.arange(128))
+    # the last, cut-off strip (225 = 28 * 8 + 1 rows): one row, walked along x
+    last = api.work_items(400, 225, 9).astype(np.int64)[224 * 400:225 * 400]
+    assert (last[:, 1] == 224).all() and np.array_equal(last[:, 0], np.arange(400))
+    # arguments nrrt_render refuses
+    assert len(api.work_items(0, 5, 1)) == 0 and len(api.work_items(5, 5, 1, rank=2, world=2)) == 0

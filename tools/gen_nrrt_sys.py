@@ -123,6 +123,8 @@ extern "C" {
     pub fn nrrt_encode_rgb8(ctx: *mut nrrt_ctx, rgb: *const f32, width: u32, height: u32, gamma: f32, flags: u32,
                             out_rgb8: *mut u8) -> c_int;
     pub fn nrrt_chunk_starts(samples_per_pixel: u32, total_pixels: u64, starts: *mut u32, max: u32) -> u32;
+    pub fn nrrt_work_items(width: u32, height: u32, samples_per_pixel: u32, rank: u32, world: u32, rows_per_block: u32,
+                           first: u32, n: u32, out: *mut u32) -> u32;
     pub fn nrrt_abi_sizeof(which: c_int) -> usize;
 }
 '''

@@ -1154,6 +1154,50 @@ int oracle_render(const oracle_scene* s, const nrrt_camera* cam, uint64_t seed, 
     return 0;
 }
 
+// The same render with the per-pixel sum taken in a GIVEN association: samples [starts[c], starts[c+1]) are summed
+// in order into a partial that starts at zero, and the partials are added in order (c = 0 .. n_chunks-1), then
+// divided by the sample count.  With one chunk this is oracle_render (the reference's plain `.sum::<DVec3>()`,
+// camera.rs:325-329).  A device that splits a pixel's samples into work items sums like this; f64 addition is not
+// associative, so a bit-for-bit comparison of a many-sample render needs the association stated (tests only).
+int oracle_render_chunked(const oracle_scene* s, const nrrt_camera* cam, uint64_t seed, uint32_t pixel_begin,
+                          uint32_t pixel_end, const uint32_t* starts, uint32_t n_chunks, float* out_rgb,
+                          uint64_t* counters, int n_threads) {
+    if (!s || !cam || !out_rgb || !starts || n_chunks == 0) return -1;
+    for (uint32_t c = 0; c < n_chunks; ++c)
+        if (starts[c + 1] <= starts[c]) return -1;
+    uint64_t paths = 0, segs = 0, aabb = 0, prim = 0;
+    const uint32_t W = cam->width;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : paths, segs, aabb, prim)
+    for (int64_t n = pixel_begin; n < (int64_t)pixel_end; ++n) {
+        Counters c;
+        uint32_t x = (uint32_t)(n % W), y = (uint32_t)(n / W);
+        V3 sum = v3(0, 0, 0);
+        for (uint32_t ch = 0; ch < n_chunks; ++ch) {
+            V3 part = v3(0, 0, 0);
+            for (uint32_t k = starts[ch]; k < starts[ch + 1]; ++k) {
+                Sampler smp{seed, (uint32_t)n, k};
+                Ray ray = get_ray(*cam, x, y, smp);
+                part = part + get_ray_color(*cam, *s->sc, ray, 0, smp, c);
+                c.paths++;
+            }
+            sum = sum + part;
+        }
+        V3 color = sum / (double)(starts[n_chunks] - starts[0]);
+        out_rgb[3 * n + 0] = (float)color.x;
+        out_rgb[3 * n + 1] = (float)color.y;
+        out_rgb[3 * n + 2] = (float)color.z;
+        paths += c.paths;
+        segs += c.segments;
+        aabb += c.aabb_tests;
+        prim += c.prim_tests;
+    }
+    if (counters) counters[0] = paths, counters[1] = segs, counters[2] = aabb, counters[3] = prim;
+    return 0;
+}
+
 // Texture::get_color for n (u,v,point) tuples: in = n x {u,v,px,py,pz}, out = n x rgb
 int oracle_texture_eval(const oracle_scene* s, uint32_t texture, const double* in, uint64_t n, double* out) {
     if (!s || texture >= s->sc->textures.size()) return -1;

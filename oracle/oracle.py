@@ -40,6 +40,8 @@ def lib() -> C.CDLL:
         L.oracle_set_trace_time.argtypes = [C.c_double]
         L.oracle_render.argtypes = [C.c_void_p, C.POINTER(A.Camera), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                     C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_render_chunked.argtypes = [C.c_void_p, C.POINTER(A.Camera), C.c_uint64, C.c_uint32, C.c_uint32,
+                                            C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_texture_eval.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
         L.oracle_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.oracle_perm_table.argtypes = [C.c_uint32, C.c_void_p]
@@ -111,6 +113,21 @@ class OracleScene:
                                  n_threads)
         if rc != 0:
             raise ValueError("oracle_render failed")
+        return out, {"paths": int(counters[0]), "segments": int(counters[1]), "aabb_tests": int(counters[2]),
+                     "prim_tests": int(counters[3])}
+
+    def render_chunked(self, cam: A.Camera, chunk_starts, seed: int = 0, pixel_range=None, n_threads: int = 0):
+        """render() with the per-pixel sum associated as given: samples [chunk_starts[c], chunk_starts[c+1]) are summed
+        in order into partials, the partials added in order (oracle_render_chunked).  One chunk = render()."""
+        W, H = cam.width, cam.height
+        p0, p1 = pixel_range if pixel_range is not None else (0, W * H)
+        st = np.ascontiguousarray(chunk_starts, dtype=np.uint32)
+        out = np.zeros((H, W, 3), dtype=np.float32)
+        counters = np.zeros(4, dtype=np.uint64)
+        rc = lib().oracle_render_chunked(self._h, C.byref(cam), seed, p0, p1, st.ctypes.data, len(st) - 1,
+                                         out.ctypes.data, counters.ctypes.data, n_threads)
+        if rc != 0:
+            raise ValueError("oracle_render_chunked failed")
         return out, {"paths": int(counters[0]), "segments": int(counters[1]), "aabb_tests": int(counters[2]),
                      "prim_tests": int(counters[3])}
 

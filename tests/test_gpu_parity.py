@@ -382,6 +382,42 @@ def test_full_frame_at_baseline_size_matches_oracle(gpu_ctx, name):
     del hs
 
 
+@pytest.mark.parametrize("name,W,H,spp,depth", [("spheres.toml", 400, 225, 100, 50), ("earth.toml", 1920, 1080, 8, None),
+                                                 ("noise.toml", 1920, 1080, 8, None)])
+def test_configs_1_and_2_at_baseline_size_match_oracle(gpu_ctx, name, W, H, spp, depth):
+    """Config 1 in full (spheres.toml 400x225, 100 spp, depth 50: 9 M paths — defocus lens, glass, metal, 488 spheres)
+    and the whole 1080p frame of config 2's two scenes (image texture through acos/atan2 sphere uv, Perlin noise) at
+    8 spp, product path against the oracle's same-stream render.
+
+    At 100 spp a pixel's samples are split into work items of 4 (nrrt_chunk_starts) whose partial sums are added in
+    order; the reference adds the 100 samples one after the other (camera.rs:325-329).  f64 addition is not associative:
+    the oracle itself gives 2 of the 90 000 pixels a different last f32 bit between the two orders.  So the GPU image is
+    compared bit for bit with the oracle summing in the work-item order, and to 1e-5 with the plain order.  Measured on
+    the B200 (profiles/r02_full_frame_parity.log): every pixel bit-equal in the work-item order on all three."""
+    kw = dict(width=W, height=H, samples_per_pixel=spp)
+    if depth is not None:
+        kw["ray_max_bounces"] = depth
+    g = load(name, **kw)
+    hs = _scene(gpu_ctx, g)
+    cam = api.camera_build(g.camera.to_builder_config())
+    osc, ocam = O.OracleScene(g), O.camera_build(g.camera.to_builder_config())
+    starts = api.chunk_starts(spp, W * H)
+    ref, cnt = osc.render_chunked(ocam, starts, seed=34)
+    seq = ref if len(starts) - 1 == spp else osc.render(ocam, seed=34)[0]   # one sample per item: the plain order
+    img, st = gpu_ctx.render(cam, seed=34, mode=A.MODE_AUTO)
+    assert st["paths"] == W * H * spp == cnt["paths"]
+    got, want = img.astype(np.float64), seq.astype(np.float64)
+    rel = np.abs(got - want) / np.maximum(1e-3, np.abs(want))
+    close = float((rel <= 1e-5).all(axis=2).mean())
+    equal = float((img == ref).all(axis=2).mean())
+    equal_seq = float((img == seq).all(axis=2).mean())
+    print(f"\nfull frame {name} {W}x{H} {spp} spp: {equal:.6f} of the pixels bit-equal (work-item order of the sum), "
+          f"{equal_seq:.6f} bit-equal / {close:.6f} within 1e-5 (plain order), segments {st['segments']} vs {cnt['segments']}")
+    assert equal >= 0.9999 and close >= 0.9999, (name, equal, close)
+    assert abs(st["segments"] - cnt["segments"]) <= 1e-5 * cnt["segments"]
+    del hs
+
+
 def test_output_stage_gamma_and_rgb8_matches_host_definition(gpu_ctx):
     """§8(f) N2: gamma_correction (image.rs:53-57) + to_rgb8 (clamp, x255, round) on the GPU vs the same formula in
     numpy f32.  powf differs by <= 2 ulp between CUDA and libm, so a value sitting on a rounding boundary may land one

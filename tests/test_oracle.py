@@ -531,3 +531,19 @@ def test_against_rust_dump():
         assert np.allclose(rust[hit_r, 8:10], ref["uv"][hit_r], rtol=4e-16, atol=4e-16), name   # acos / atan2
         checked += 1
     assert checked >= 2
+
+
+def test_render_chunked_is_render_with_the_sum_reassociated():
+    """oracle_render_chunked: one chunk, or one sample per chunk, is the plain sequential sum of render(); any other
+    split changes at most the last bits (same paths, same counts)."""
+    g = load("spheres.toml", width=40, height=22, samples_per_pixel=24)
+    sc = O.OracleScene(g)
+    cam = O.camera_build(g.camera.to_builder_config())
+    a, ca = sc.render(cam, seed=3)
+    b, cb = sc.render_chunked(cam, [0, 24], seed=3)
+    c, cc = sc.render_chunked(cam, list(range(25)), seed=3)
+    d, cd = sc.render_chunked(cam, [0, 5, 10, 15, 20, 24], seed=3)
+    assert np.array_equal(a, b) and np.array_equal(a, c) and ca == cb == cc == cd
+    assert np.allclose(a, d, rtol=3e-7, atol=0)
+    with pytest.raises(ValueError):
+        sc.render_chunked(cam, [0, 5, 5, 24], seed=3)

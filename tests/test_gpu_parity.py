@@ -357,6 +357,29 @@ def test_full_width_strip_at_baseline_size_matches_oracle(gpu_ctx, name):
     del hs
 
 
+@pytest.mark.parametrize("name", ["cornell-box-scene.json", "utah-teapot-scene.json"])
+def test_benchmark_workload_strip_matches_oracle(gpu_ctx, name):
+    """The benchmark workload itself — 1920x1080, 1024 spp, depth 50, the render bench.py times (config 3) and config 4 —
+    checked on an 8-row strip through the middle (15 360 pixels, 15.7 M paths): the oracle renders the strip with the
+    same Philox streams, summing each pixel in the work-item order (28 items: 27 x 37 samples + 25), and the rows of the
+    full GPU image must equal it bit for bit."""
+    W, H, spp, y0 = 1920, 1080, 1024, 536
+    g = load(name, width=W, height=H, samples_per_pixel=spp, ray_max_bounces=50)
+    hs = _scene(gpu_ctx, g)
+    cam = api.camera_build(g.camera.to_builder_config())
+    starts = api.chunk_starts(spp, W * H)
+    assert len(starts) - 1 == 28
+    ref, cnt = O.OracleScene(g).render_chunked(O.camera_build(g.camera.to_builder_config()), starts, seed=0,
+                                               pixel_range=(y0 * W, (y0 + 8) * W))
+    img, st = gpu_ctx.render(cam, seed=0, mode=A.MODE_AUTO)
+    assert st["paths"] == W * H * spp and cnt["paths"] == 8 * W * spp
+    equal = float((img[y0:y0 + 8] == ref[y0:y0 + 8]).all(axis=2).mean())
+    print(f"\nbenchmark workload strip {name}: {equal:.6f} of the strip's pixels bit-equal, {st['segments']} segments "
+          f"in {st['device_ms']:.1f} ms on the device")
+    assert equal >= 0.9999, (name, equal)
+    del hs
+
+
 @pytest.mark.parametrize("name", ["cornell-box-scene.json", "utah-teapot-scene.json", "cornell-teapot-scene.json"])
 def test_full_frame_at_baseline_size_matches_oracle(gpu_ctx, name):
     """The WHOLE 1920x1080 frame of configs 3 / 4 / 5 at depth 50 and 8 spp (16.6 M paths each) against the oracle's

@@ -380,6 +380,33 @@ def test_benchmark_workload_strip_matches_oracle(gpu_ctx, name):
     del hs
 
 
+def test_config5_at_its_own_size_strip_matches_oracle(gpu_ctx):
+    """Config 5 at its image size: Cornell box + teapot, 3840x2160, depth 50, at 64 spp (work items of 8 samples, as at
+    4096 spp there are 8 items per pixel).  An 8-row strip of the full GPU image, and the row of it that rank 5 of 8
+    renders in a shared image (single-row interleave, packed output), against the oracle in the work-item order."""
+    from nr_ray_tracer_b200 import distributed as D
+    W, H, spp, y0 = 3840, 2160, 64, 1076
+    g = load("cornell-teapot-scene.json", width=W, height=H, samples_per_pixel=spp, ray_max_bounces=50)
+    hs = _scene(gpu_ctx, g)
+    cam = api.camera_build(g.camera.to_builder_config())
+    starts = api.chunk_starts(spp, W * H)
+    assert starts == list(range(0, 65, 8)) and len(api.chunk_starts(4096, W * H)) - 1 == 8
+    ref, cnt = O.OracleScene(g).render_chunked(O.camera_build(g.camera.to_builder_config()), starts, seed=5,
+                                               pixel_range=(y0 * W, (y0 + 8) * W))
+    img, st = gpu_ctx.render(cam, seed=5, mode=A.MODE_AUTO)
+    assert st["paths"] == W * H * spp and st["mode"] == A.MODE_POOL
+    equal = float((img[y0:y0 + 8] == ref[y0:y0 + 8]).all(axis=2).mean())
+    rows = D.owned_rows(H, 5, 8, 1)
+    part = np.full((len(rows), W, 3), np.nan, dtype=np.float32)
+    _, sp = gpu_ctx.render(cam, out=part, seed=5, mode=A.MODE_AUTO, rank=5, world=8, rows_per_block=1, packed=True)
+    assert sp["pixels"] == len(rows) * W == 270 * W
+    print(f"\nconfig 5 at 3840x2160, 64 spp: {equal:.6f} of the strip's pixels bit-equal, {st['segments']} segments in "
+          f"{st['device_ms']:.1f} ms; rank 5 of 8: {sp['segments']} segments in {sp['device_ms']:.1f} ms")
+    assert equal >= 0.9999
+    assert np.array_equal(part, img[rows])
+    del hs
+
+
 @pytest.mark.parametrize("name", ["cornell-box-scene.json", "utah-teapot-scene.json", "cornell-teapot-scene.json"])
 def test_full_frame_at_baseline_size_matches_oracle(gpu_ctx, name):
     """The WHOLE 1920x1080 frame of configs 3 / 4 / 5 at depth 50 and 8 spp (16.6 M paths each) against the oracle's

@@ -20,7 +20,7 @@
 
 #include "../../include/nrrt.h"
 
-static void die(const std::string& m) {
+[[noreturn]] static void die(const std::string& m) {
     std::fprintf(stderr, "Error: %s\n", m.c_str());
     std::exit(1);
 }

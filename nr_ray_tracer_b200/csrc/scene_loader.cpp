@@ -900,7 +900,7 @@ nrrt_loaded_scene* nrrt_load_scene(const char* path, const char* base_dir) {
     try {
         auto ls = std::make_unique<nrrt_loaded_scene>();
         ValuePtr root = load_scene_file(path);
-        Builder b{ls->g, base_dir ? std::string(base_dir) : std::string()};
+        Builder b{ls->g, base_dir ? std::string(base_dir) : std::string(), {}};
         b.include_stack.push_back(path);
         ls->g.root = b.build_aux(*root, false, 0);
         read_camera(*root, ls->cam);
